@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the TC-ELBO hot path (BASELINE.json metric: "TC-ELBO fwd+bwd log-densities/s (B^2*D)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--zdim D]
+
+A "step" is one compute_kl_loss-equivalent evaluation: reparameterize + KL + TC
+(minibatch stratified sampling) + (beta-1)*TC + KL, mean-reduced, and its backward to mu / logvar.
+Workload at every N: BASELINE configs[2] at the size the north-star target is quoted on -- synthetic
+latents, GLOBAL batch 8192, z_dim 128 (strong scaling: rank r owns rows [r*B/N, (r+1)*B/N), mu is
+all-gathered over NCCL before the sweep and its gradient reduce-scattered after it).
+
+Prints ONE JSON line on rank 0 (see the keys below).  `--impl reference` times the CPU oracle port of
+the reference's implementation on the host cores (the reference itself is Python/torch and cannot travel).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+METRIC = "tc_elbo_fwd_bwd_log_densities_per_s"
+UNIT = "log-densities/s"
+DATASET_SIZE = 16704          # UkiyoE-sized N
+BETA = 0.5
+CPU_SAMPLE_B = 1024           # bounded CPU sample: B=1024, D=128 (the reference keeps 4*B^2*D*4 bytes = 2 GiB for backward)
+
+
+def synthetic_latents(b, d, seed=1234):
+    """mu ~ N(0,1), logvar ~ N(-2,1), eps ~ N(0,1): about 5 % of the log-densities hit the -50 clamp."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    mu = torch.randn(b, d, generator=g)
+    lv = -2.0 + torch.randn(b, d, generator=g)
+    eps = torch.randn(b, d, generator=g)
+    return mu, lv, eps
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_step(mu, lv, eps, n, beta):
+    from oracle import tc_oracle as O
+    mu = mu.detach().requires_grad_(True)
+    lv = lv.detach().requires_grad_(True)
+    z = O.reparameterize(mu, lv, eps)
+    loss = O.kl_loss_simple(z, mu, lv, n, beta, "mean")
+    loss.backward()
+    return loss.item()
+
+
+def time_cpu(b, d, steps, warmup):
+    mu, lv, eps = synthetic_latents(b, d)
+    for _ in range(warmup):
+        cpu_step(mu, lv, eps, DATASET_SIZE, BETA)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_step(mu, lv, eps, DATASET_SIZE, BETA)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    b, d = CPU_SAMPLE_B, args.zdim
+    times = time_cpu(b, d, args.steps, args.warmup)
+    t = sum(times) / len(times)
+    value = b * b * d / t
+    cores = torch.get_num_threads()
+    sample = (f"B={b}, D={d}, N={DATASET_SIZE}: reparameterize + kl_divergence + total_correlation + backward, fp32, "
+              f"oracle port of the reference's op sequence (oracle/tc_oracle.py), {cores} torch threads of {os.cpu_count()} cpus")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"tc_microbench: global batch 8192, z_dim {d} (timed on a bounded CPU sample: B={b})",
+                   "sample_batch": b, "z_dim": d, "dataset_size": DATASET_SIZE, "beta": BETA},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), line.strip()))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, smax, power, reasons = [], [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from intro_tc_vae_b200 import _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the TC-ELBO path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    lib = _lib.load()
+
+    B, D, N = args.batch, args.zdim, DATASET_SIZE
+    assert B % world == 0, "global batch must divide by the number of ranks"
+    b_loc = B // world
+    lo = rank * b_loc
+    mu_c, lv_c, eps_c = synthetic_latents(B, D)
+    mu_h = mu_c[lo:lo + b_loc].contiguous().pin_memory()
+    lv_h = lv_c[lo:lo + b_loc].contiguous().pin_memory()
+    eps_h = eps_c[lo:lo + b_loc].contiguous().pin_memory()
+    mu = mu_h.to(dev).requires_grad_(True)
+    lv = lv_h.to(dev).requires_grad_(True)
+    eps = eps_h.to(dev)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step(mu_t, lv_t, eps_t):
+        mu_t.grad = None
+        lv_t.grad = None
+        z = ops.reparameterize(mu_t, lv_t, eps_t)
+        kl = ops.kl_divergence(lv_t, mu_t, reduce="mean")
+        tc = ops.total_correlation(z, mu_t, lv_t, N, reduce="mean", group=group)
+        loss = (BETA - 1.0) * tc + kl
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        step(mu, lv, eps)
+    barrier()
+
+    # ---- timed: K steps, inputs resident in HBM, L2 flushed between steps (outside the event pairs)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = lib.tcelbo_launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush_buf.fill_(k & 0xFF)
+        starts[k].record()
+        step(mu, lv, eps)
+        stops[k].record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = lib.tcelbo_launch_count() - launches0
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    total_ms = max_over_ranks(dev_ms)
+    ms_per_step = total_ms / args.steps
+    value = B * B * D / (ms_per_step * 1e-3)
+
+    # ---- e2e: the same step through the public API with HOST buffers (H2D of mu/logvar/eps, D2H of loss + grads)
+    gmu_h = torch.empty(b_loc, D).pin_memory()
+    glv_h = torch.empty(b_loc, D).pin_memory()
+    loss_h = torch.empty(1).pin_memory()
+
+    def e2e_step():
+        mu_d = mu_h.to(dev, non_blocking=True).requires_grad_(True)
+        lv_d = lv_h.to(dev, non_blocking=True).requires_grad_(True)
+        eps_d = eps_h.to(dev, non_blocking=True)
+        loss = step(mu_d, lv_d, eps_d)
+        gmu_h.copy_(mu_d.grad, non_blocking=True)
+        glv_h.copy_(lv_d.grad, non_blocking=True)
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush_buf.fill_(k & 0xFF)
+        e_starts[k].record()
+        e2e_step()
+        e_stops[k].record()
+    barrier()
+    e2e_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(e_starts, e_stops))) / args.steps
+    e2e_value = B * B * D / (e2e_ms * 1e-3)
+    t_region_end = time.perf_counter()
+    if rank == 0:
+        time.sleep(0.2)
+        sampler.stop()
+    clocks = sampler.summary(t_wall0, t_region_end) if rank == 0 else {}
+
+    # ---- roofline of the dominant kernels, timed live with CUDA events on the launching stream
+    roof = None
+    if rank == 0:
+        cur = torch.cuda.current_stream(dev)
+        kern_ms = {}
+        for kid, name in ((1, "tc_fwd_kernel"), (2, "tc_bwd_row_kernel"), (3, "tc_bwd_col_kernel")):
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record(cur); ev1.record(cur)               # materialise the underlying cudaEvent_t handles
+            ts = []
+            for k in range(min(args.steps, 5)):
+                flush_buf.fill_(k)
+                _lib.check(lib.tcelbo_profile_events(kid, ev0.cuda_event, ev1.cuda_event), "profile_events")
+                step(mu, lv, eps)
+                torch.cuda.synchronize()
+                lib.tcelbo_profile_events(0, None, None)
+                ts.append(ev0.elapsed_time(ev1))
+            kern_ms[name] = sum(ts) / len(ts)
+        # SFU saturation probe in the same job (empirical ex2 peak)
+        scratch = torch.zeros(16, device=dev)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        iters, ctas = 4096, sms * 8
+        lib.tcelbo_ex2_peak(scratch.data_ptr(), 64, ctas, cur.cuda_stream)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        lib.tcelbo_ex2_peak(scratch.data_ptr(), iters, ctas, cur.cuda_stream)
+        p1.record()
+        torch.cuda.synchronize()
+        ex2_measured = ctas * 256 * 8 * iters / (p0.elapsed_time(p1) * 1e-3)
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        peak_nominal = sms * 16 * 1965.0e6                     # 16 MUFU lanes per SM per clock at the max SM clock
+        peak_at_clock = sms * 16 * sm_mhz * 1e6
+        rows_loc = b_loc
+        alg_fwd = rows_loc * B * D + rows_loc * B              # ex2 per forward sweep on this rank
+        dom = max(kern_ms, key=kern_ms.get)
+        achieved = alg_fwd / (kern_ms[dom] * 1e-3)
+        hbm_bytes = 48.0 * B * D                               # algorithmic bytes of one evaluation
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roof = {
+            "bound": "sfu", "kernel": dom, "achieved": achieved / 1e9, "peak": peak_nominal / 1e9, "unit": "Gex2/s",
+            "frac": achieved / peak_nominal, "traffic": None,
+            "peak_note": "148 SM x 16 MUFU/clk x 1.965 GHz (max SM clock); ex2_measured_gps is the in-job saturation probe",
+            "ex2_measured_gps": ex2_measured / 1e9, "frac_of_measured_ex2": achieved / ex2_measured,
+            "peak_at_observed_clock_gps": peak_at_clock / 1e9,
+            "kernel_ms": kern_ms,
+            "step_algorithmic_ex2": 2 * B * B * D + 2 * B * B,
+            "step_frac_of_sfu_peak": (2 * B * B * D + 2 * B * B) / world / (ms_per_step * 1e-3) / peak_nominal,
+            "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (ms_per_step * 1e-3) / 1e9,
+                    "peak_gbs": hbm_peak, "peak_source": "measured" if peaks else "fallback",
+                    "frac": hbm_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak},
+        }
+
+    # ---- CPU baseline (rank 0, N == 1 only): bounded sample of the same workload on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times = time_cpu(CPU_SAMPLE_B, D, steps=3, warmup=1)
+        t = min(times)
+        cores = torch.get_num_threads()
+        cpu = {"value": CPU_SAMPLE_B * CPU_SAMPLE_B * D / t, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"B={CPU_SAMPLE_B}, D={D}, N={N}: same step (reparameterize + KL + TC + backward) through the oracle "
+                         f"port of the reference's op sequence, fp32, best of 3, {cores} torch threads of {os.cpu_count()} cpus"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"tc_microbench (BASELINE configs[2]): global batch {B}, z_dim {D}, N={N}, beta={BETA}, "
+                                   "MSS estimator, row-variance density, fwd+bwd",
+                       "global_batch": B, "z_dim": D, "rows_per_gpu": b_loc, "parallelism": f"row-shard x{world}",
+                       "l2": "flushed between timed steps by writing a 256 MiB buffer (outside the event pairs)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 3 * b_loc * D * 4, "d2h_bytes_per_step": 2 * b_loc * D * 4 + 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "wall_s_timed_region": t_wall1 - t_wall0,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8192, help="GLOBAL batch (rows are sharded over the ranks)")
+    ap.add_argument("--zdim", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,145 @@
+/*
+ * tcelbo.h -- C ABI of the B200-native total-correlation ELBO path (libtcelbo.so).
+ *
+ * Drop-in boundary for the hot path of meffmadd/intro-tc-vae (file:line relative to the reference
+ * repository).  The reference is pure Python/PyTorch with no FFI of its own; these entry points are
+ * what a binding for the path would bind, one per reference function:
+ *
+ *   tcelbo_forward / tcelbo_backward    ops.py:52-89   total_correlation
+ *                                       ops.py:15-21   gaussian_log_density_torch   (TCELBO_VAR_ROW)
+ *                                       ops.py:24-29   gaussian_log_density         (TCELBO_VAR_COL,
+ *                                                      as called at solvers/tc.py:114-116)
+ *                                       ops.py:32-49   log_importance_weight_matrix (folded in: 3 scalars)
+ *                                       ops.py:104-115 minibatch_stratified_sampling (TCELBO_EST_MSS)
+ *                                       ops.py:92-101  minibatch_weighted_sampling   (TCELBO_EST_MWS)
+ *   tcelbo_kl_forward / _backward       ops.py:136-163 kl_divergence / kl_no_reduce
+ *   tcelbo_reparam_forward / _backward  ops.py:166-185 reparameterize (eps supplied by the caller so
+ *                                                      that torch's device Philox stream is preserved)
+ *   tcelbo_rowdensity_forward/_backward ops.py:24-29 summed over dim 1, the row-wise log q(z|x) and
+ *                                       log p(z) terms of solvers/tc.py:107,112
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers to fp32 unless stated; `ld*` are row pitches in ELEMENTS
+ *     (the encoder returns mu/logvar as chunk views with pitch 2*D, models.py:242-244).
+ *   - Nothing is allocated, no host synchronisation happens, every call is asynchronous on `stream`
+ *     (a cudaStream_t passed as void*) and CUDA-graph capturable.  Scratch comes from the caller:
+ *     query tcelbo_workspace_bytes() and pass a 256-byte aligned buffer.  The buffer written by
+ *     tcelbo_forward(flags | TCELBO_SAVE_FOR_BACKWARD) must be handed unchanged to tcelbo_backward.
+ *   - Return value: 0 on success, a TCELBO_ERR_* code otherwise; tcelbo_last_error() returns a
+ *     thread-local message.  Nothing throws across the boundary.
+ *   - Sharding: a rank owns global rows [row_offset, row_offset + b_loc) of a global
+ *     batch of b_glob columns; `mu_all` (and `logvar` for TCELBO_VAR_COL) hold all b_glob rows after
+ *     the caller's all-gather; grad_mu_all is this rank's partial [b_glob, D] to be reduce-scattered.
+ *     Single GPU: b_loc == b_glob, row_offset == 0.
+ *   - Error behaviour mirrored from the reference: b_glob == 1 is rejected (ZeroDivisionError at
+ *     ops.py:44, raised by the Python wrapper); dataset_size < b_glob-1 yields NaN outputs (log of a
+ *     negative weight), not an error.
+ */
+#ifndef TCELBO_H_
+#define TCELBO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCELBO_VERSION 1
+
+/* flags */
+#define TCELBO_EST_MSS            0u   /* minibatch stratified sampling (active in the reference) */
+#define TCELBO_EST_MWS            1u   /* minibatch weighted sampling */
+#define TCELBO_VAR_ROW            0u   /* log q(z_i | mu_j, var_i), variance floored at 1e-4 (ops.py:15-21,80-82) */
+#define TCELBO_VAR_COL            2u   /* log q(z_i | mu_j, var_j), no floor (ops.py:24-29, solvers/tc.py:114-116) */
+#define TCELBO_SAVE_FOR_BACKWARD  4u   /* forward keeps what backward needs in the workspace */
+
+/* error codes */
+#define TCELBO_OK               0
+#define TCELBO_ERR_INVALID      1      /* bad argument (message says which) */
+#define TCELBO_ERR_CUDA         2      /* a CUDA runtime call failed */
+#define TCELBO_ERR_WORKSPACE    3      /* workspace too small or misaligned */
+#define TCELBO_ERR_UNSUPPORTED  4      /* shape outside the built kernels (D > 512) */
+
+int         tcelbo_version(void);
+const char* tcelbo_last_error(void);
+
+/* Bytes of scratch needed by forward (+ backward when TCELBO_SAVE_FOR_BACKWARD is set). */
+size_t tcelbo_workspace_bytes(int b_loc, int b_glob, int d, uint32_t flags);
+
+/*
+ * Forward: for each local row i
+ *   log_qz_prod[i] = sum_d LSE_j( logw_ij + lp_ijd )        (log prod_d q(z_d))
+ *   log_qz[i]      =       LSE_j( logw_ij + sum_d lp_ijd )   (log q(z))
+ * total correlation is log_qz - log_qz_prod (ops.py:86-89).
+ *   z       [b_loc , D]  sampled latents of the local rows
+ *   mu_all  [b_glob, D]  encoder means of ALL rows (columns j)
+ *   logvar  [b_loc , D]  for TCELBO_VAR_ROW (local rows); [b_glob, D] for TCELBO_VAR_COL
+ */
+int tcelbo_forward(const float* z, int64_t ldz,
+                   const float* mu_all, int64_t ldmu,
+                   const float* logvar, int64_t ldlv,
+                   int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
+                   float* log_qz, float* log_qz_prod,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Backward of tcelbo_forward given g_log_qz[i] = dLoss/dlog_qz[i], g_log_qz_prod[i] likewise.
+ * The B x B x D log-densities are recomputed tile by tile, never stored.
+ *   grad_z       [b_loc , D]
+ *   grad_mu_all  [b_glob, D]  (partial over this rank's rows)
+ *   grad_logvar  [b_loc , D] for TCELBO_VAR_ROW, [b_glob, D] (partial) for TCELBO_VAR_COL
+ * Same z / mu_all / logvar / sizes / flags as the forward call whose workspace is passed.
+ */
+int tcelbo_backward(const float* z, int64_t ldz,
+                    const float* mu_all, int64_t ldmu,
+                    const float* logvar, int64_t ldlv,
+                    int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
+                    const float* g_log_qz, const float* g_log_qz_prod,
+                    float* grad_z, int64_t ldgz,
+                    float* grad_mu_all, int64_t ldgmu,
+                    float* grad_logvar, int64_t ldglv,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* kl_rows[i] = -0.5 * sum_d (1 + logvar - exp(logvar) - mu^2)   (ops.py:161-163; argument order logvar, mu) */
+int tcelbo_kl_forward(const float* logvar, int64_t ldlv, const float* mu, int64_t ldmu,
+                      int b, int d, float* kl_rows, void* stream);
+/* grad_logvar = g_rows[i] * 0.5*(exp(logvar)-1), grad_mu = g_rows[i] * mu */
+int tcelbo_kl_backward(const float* logvar, int64_t ldlv, const float* mu, int64_t ldmu,
+                       const float* g_rows, int b, int d,
+                       float* grad_logvar, int64_t ldglv, float* grad_mu, int64_t ldgmu, void* stream);
+
+/* z = mu + eps * exp(0.5*logvar)   (ops.py:183-185) */
+int tcelbo_reparam_forward(const float* mu, int64_t ldmu, const float* logvar, int64_t ldlv,
+                           const float* eps, int64_t ldeps, int b, int d, float* z, int64_t ldz, void* stream);
+/* grad_mu = g_z ; grad_logvar = g_z * eps * 0.5*exp(0.5*logvar) */
+int tcelbo_reparam_backward(const float* logvar, int64_t ldlv, const float* eps, int64_t ldeps,
+                            const float* g_z, int64_t ldgz, int b, int d,
+                            float* grad_mu, int64_t ldgmu, float* grad_logvar, int64_t ldglv, void* stream);
+
+/*
+ * Row-wise Gaussian log-density summed over D (ops.py:24-29 + .sum(dim=1), solvers/tc.py:107,112):
+ *   out[i] = sum_d max(-0.5*((x-mu)^2*exp(-logvar) + logvar + log 2pi), -50)
+ * mu == NULL and logvar == NULL mean the standard normal prior (zeros).
+ */
+int tcelbo_rowdensity_forward(const float* x, int64_t ldx, const float* mu, int64_t ldmu,
+                              const float* logvar, int64_t ldlv, int b, int d, float* out, void* stream);
+int tcelbo_rowdensity_backward(const float* x, int64_t ldx, const float* mu, int64_t ldmu,
+                               const float* logvar, int64_t ldlv, const float* g_rows, int b, int d,
+                               float* grad_x, int64_t ldgx, float* grad_mu, int64_t ldgmu,
+                               float* grad_logvar, int64_t ldglv, void* stream);
+
+/* ---- diagnostics used by bench.py (no reference counterpart) --------------------------------------- */
+/* Number of kernels this library has launched in the calling process so far. */
+long long tcelbo_launch_count(void);
+/* Bracket every later launch of one kernel class (1 = forward sweep, 2 = backward row sweep,
+ * 3 = backward column sweep, 0 = off) with cudaEventRecord(start) / cudaEventRecord(stop) on its stream;
+ * the events are cudaEvent_t handles owned by the caller. */
+int tcelbo_profile_events(int kernel_id, void* start_event, void* stop_event);
+/* MUFU.EX2 saturation probe: `ctas` blocks of 256 threads, 8*iters dependent-chain ex2 per thread. */
+int tcelbo_ex2_peak(float* scratch, int iters, int ctas, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCELBO_H_ */

@@ -1,0 +1,83 @@
+"""ctypes binding of libtcelbo.so (C ABI declared in include/tcelbo.h).
+
+There is deliberately no fallback: if the shared library is missing or cannot be loaded, every op
+of this package raises.  Build it with ``python -m intro_tc_vae_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p, POINTER
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libtcelbo.so")
+
+# flags (include/tcelbo.h)
+EST_MSS = 0
+EST_MWS = 1
+VAR_ROW = 0
+VAR_COL = 2
+SAVE_FOR_BACKWARD = 4
+
+ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 1, 2, 3, 4
+
+_f = c_void_p          # device pointers are passed as integers (tensor.data_ptr())
+
+_SIGNATURES = {
+    "tcelbo_version": (c_int, []),
+    "tcelbo_last_error": (c_char_p, []),
+    "tcelbo_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_uint32]),
+    "tcelbo_forward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64, c_uint32,
+                               _f, _f, c_void_p, c_size_t, c_void_p]),
+    "tcelbo_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64, c_uint32,
+                                _f, _f, _f, c_int64, _f, c_int64, _f, c_int64, c_void_p, c_size_t, c_void_p]),
+    "tcelbo_kl_forward": (c_int, [_f, c_int64, _f, c_int64, c_int, c_int, _f, c_void_p]),
+    "tcelbo_kl_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int, c_int, _f, c_int64, _f, c_int64, c_void_p]),
+    "tcelbo_reparam_forward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_int64, c_void_p]),
+    "tcelbo_reparam_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_int64, _f, c_int64,
+                                        c_void_p]),
+    "tcelbo_rowdensity_forward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_void_p]),
+    "tcelbo_rowdensity_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, _f, c_int, c_int,
+                                           _f, c_int64, _f, c_int64, _f, c_int64, c_void_p]),
+    "tcelbo_launch_count": (ctypes.c_longlong, []),
+    "tcelbo_profile_events": (c_int, [c_int, c_void_p, c_void_p]),
+    "tcelbo_ex2_peak": (c_int, [_f, c_int, c_int, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class TcelboError(RuntimeError):
+    """A libtcelbo.so entry point returned a non-zero status."""
+
+
+def load() -> ctypes.CDLL:
+    """Load libtcelbo.so once; raises if it is absent (no CPU / eager fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m intro_tc_vae_b200.build` "
+            "(the TC-ELBO ops have no fallback implementation)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here means the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status == 0:
+        return
+    msg = load().tcelbo_last_error()
+    msg = msg.decode() if msg else ""
+    if status == ERR_UNSUPPORTED:
+        raise NotImplementedError(f"{what}: {msg}")
+    if status in (ERR_INVALID, ERR_WORKSPACE):
+        raise ValueError(f"{what}: {msg}")
+    raise TcelboError(f"{what} failed with status {status}: {msg}")

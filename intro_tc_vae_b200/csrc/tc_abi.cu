@@ -1,0 +1,273 @@
+// C ABI of libtcelbo.so (include/tcelbo.h).  Plain pointers and sizes only; no torch types.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "tc_instr.h"
+#include "tc_kernels.h"
+#include "tc_rowops.h"
+#include "tcelbo.h"
+
+using namespace tcelbo;
+
+namespace tcelbo {
+Instr& instr() { static Instr in; return in; }
+}
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char* what) {
+    return fail(TCELBO_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached > 0) return cached;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
+        cached = sms;
+        return sms;
+    }
+    (void)cudaGetLastError();
+    return 148;                                   // B200; only reached when no device is visible (size queries on a CPU box)
+}
+
+// Importance weights the way the reference forms them (ops.py:42-49): python doubles rounded into an
+// fp32 tensor, then log().  Only three distinct values exist, so the B x B matrix is never built.
+Weights make_weights(int b_glob, int64_t n, uint32_t flags) {
+    Weights w;
+    w.b_glob = b_glob;
+    if (flags & TCELBO_EST_MWS) {                 // ops.py:96,99: subtract log(B*N)
+        w.mss = 0;
+        w.r_n = w.r_s = 1.0f; w.l2r_n = w.l2r_s = 0.0f;
+        w.lw_u = (float)(-std::log((double)b_glob * (double)n));
+        return w;
+    }
+    const double m = (double)(b_glob - 1);
+    const float w_u = (float)(1.0 / m);
+    const float w_n = (float)(1.0 / (double)n);
+    const float w_s = (float)(((double)n - m) / ((double)n * m));
+    w.mss = 1;
+    w.lw_u = logf(w_u);
+    const double rn = (double)w_n / (double)w_u, rs = (double)w_s / (double)w_u;
+    w.r_n = (float)rn;  w.l2r_n = (float)std::log2(rn);
+    if (w_s < 0.0f) {                             // N < B-1: log of a negative weight is NaN in the reference
+        w.r_s = NAN; w.l2r_s = NAN;
+    } else {
+        w.r_s = (float)rs; w.l2r_s = (float)std::log2(rs);    // rs == 0 -> -inf, rho 0: matches log(0) = -inf
+    }
+    return w;
+}
+
+bool aligned256(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 255u) == 0; }
+
+template <typename T> T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
+
+int check_common(const float* z, const float* mu_all, const float* logvar, int b_loc, int b_glob, int row_offset, int d,
+                 int64_t dataset_size, uint32_t flags, int64_t ldz, int64_t ldmu, int64_t ldlv) {
+    if (!z || !mu_all || !logvar) return fail(TCELBO_ERR_INVALID, "null input pointer");
+    if (b_loc < 1 || b_glob < 1 || d < 1) return fail(TCELBO_ERR_INVALID, "b_loc, b_glob and d must be positive");
+    if (b_glob < 2 && !(flags & TCELBO_EST_MWS)) return fail(TCELBO_ERR_INVALID, "b_glob == 1: the stratified weight divides by B-1 (ZeroDivisionError at ops.py:44)");
+    if (row_offset < 0 || (int64_t)row_offset + b_loc > b_glob) return fail(TCELBO_ERR_INVALID, "rows [row_offset, row_offset+b_loc) exceed b_glob");
+    if (dataset_size < 1) return fail(TCELBO_ERR_INVALID, "dataset_size must be positive");
+    if (ldz < d || ldmu < d || ldlv < d) return fail(TCELBO_ERR_INVALID, "row pitch smaller than d");
+    if (d > 512) return fail(TCELBO_ERR_UNSUPPORTED, "d = %d > 512 is outside the built kernels", d);
+    if (flags & TCELBO_VAR_COL) return fail(TCELBO_ERR_UNSUPPORTED, "TCELBO_VAR_COL is not built yet");
+    return TCELBO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tcelbo_version(void) { return TCELBO_VERSION; }
+
+const char* tcelbo_last_error(void) { return g_last_error.c_str(); }
+
+size_t tcelbo_workspace_bytes(int b_loc, int b_glob, int d, uint32_t flags) {
+    Plan p;
+    if (!make_plan(p, b_loc, b_glob, d, flags, sm_count())) return 0;
+    return p.total_bytes;
+}
+
+int tcelbo_forward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                   int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
+                   float* log_qz, float* log_qz_prod, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv)) return rc;
+    if (!log_qz || !log_qz_prod) return fail(TCELBO_ERR_INVALID, "null output pointer");
+    Plan p;
+    if (!make_plan(p, b_loc, b_glob, d, flags, sm_count())) return fail(TCELBO_ERR_INVALID, "cannot plan this shape");
+    if (!workspace || workspace_bytes < p.total_bytes || !aligned256(workspace))
+        return fail(TCELBO_ERR_WORKSPACE, "workspace must be 256-byte aligned and at least %zu bytes (got %zu)", p.total_bytes, workspace_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Weights w = make_weights(b_glob, dataset_size, flags);
+    cudaError_t e;
+
+    float* mu_pad = at<float>(workspace, p.off_mu);
+    float* zs = at<float>(workspace, p.off_zs);
+    float* ns = at<float>(workspace, p.off_ns);
+    float* qmax = at<float>(workspace, p.off_qmax);
+    float* shift = at<float>(workspace, p.off_shift);
+    float* vr = at<float>(workspace, p.off_vr);
+    float* Spart = at<float>(workspace, p.off_scratch);
+    float* Jpart = Spart + (size_t)p.n_js_fwd * p.bl_pad * p.dp;
+
+    if ((e = launch_col_prep(mu_all, ldmu, p, mu_pad, st)) != cudaSuccess) return fail_cuda(e, "col_prep");
+    if ((e = launch_row_prep(z, ldz, logvar, ldlv, p, zs, ns, qmax, shift, vr, st)) != cudaSuccess) return fail_cuda(e, "row_prep");
+
+    FwdArgs fa;
+    fa.zs = zs; fa.ns = ns; fa.qmax = qmax; fa.mu_pad = mu_pad;
+    fa.s2 = p.save ? at<float>(workspace, p.off_s2) : nullptr; fa.ld_s2 = p.ld_s2;
+    fa.Spart = Spart; fa.Jpart = Jpart;
+    fa.b_loc = b_loc; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.row_offset = row_offset; fa.js_len = p.js_len_fwd;
+    fa.w = w;
+    if ((e = launch_fwd(p, fa, st)) != cudaSuccess) return fail_cuda(e, "tc_fwd");
+
+    FinArgs fin;
+    fin.Spart = Spart; fin.Jpart = Jpart; fin.shift = shift;
+    fin.S = at<float>(workspace, p.off_S); fin.J2 = at<float>(workspace, p.off_J2);
+    fin.log_qz = log_qz; fin.log_qz_prod = log_qz_prod;
+    fin.b_loc = b_loc; fin.bl_pad = p.bl_pad; fin.d = d; fin.dp = p.dp; fin.n_js = p.n_js_fwd; fin.lw_u = w.lw_u;
+    if ((e = launch_fwd_finalize(p, fin, st)) != cudaSuccess) return fail_cuda(e, "fwd_finalize");
+    return TCELBO_OK;
+}
+
+int tcelbo_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                    int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
+                    const float* g_log_qz, const float* g_log_qz_prod,
+                    float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv)) return rc;
+    if (!(flags & TCELBO_SAVE_FOR_BACKWARD)) return fail(TCELBO_ERR_INVALID, "backward needs the workspace of a forward run with TCELBO_SAVE_FOR_BACKWARD");
+    if (!g_log_qz || !g_log_qz_prod || !grad_z || !grad_mu_all || !grad_logvar) return fail(TCELBO_ERR_INVALID, "null gradient pointer");
+    if (ldgz < d || ldgmu < d || ldglv < d) return fail(TCELBO_ERR_INVALID, "gradient row pitch smaller than d");
+    Plan p;
+    if (!make_plan(p, b_loc, b_glob, d, flags, sm_count())) return fail(TCELBO_ERR_INVALID, "cannot plan this shape");
+    if (!workspace || workspace_bytes < p.total_bytes || !aligned256(workspace))
+        return fail(TCELBO_ERR_WORKSPACE, "workspace must be the %zu-byte buffer forward wrote (got %zu)", p.total_bytes, workspace_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Weights w = make_weights(b_glob, dataset_size, flags);
+    cudaError_t e;
+
+    const float* mu_pad = at<float>(workspace, p.off_mu);
+    const float* zs = at<float>(workspace, p.off_zs);
+    const float* ns = at<float>(workspace, p.off_ns);
+    const float* qmax = at<float>(workspace, p.off_qmax);
+    const float* vr = at<float>(workspace, p.off_vr);
+    const float* S = at<float>(workspace, p.off_S);
+    const float* J2 = at<float>(workspace, p.off_J2);
+    const float* s2 = at<float>(workspace, p.off_s2);
+    float* gps = at<float>(workspace, p.off_gps);
+    float* gj = at<float>(workspace, p.off_gj);
+    float* Apart = at<float>(workspace, p.off_scratch);
+    float* CRpart = Apart + (size_t)p.n_js_bwr * p.bl_pad * p.dp;
+    float* Gpart = CRpart + (size_t)p.n_js_bwr * p.bl_pad * p.dp;
+
+    if ((e = launch_bwd_prep(p, g_log_qz, g_log_qz_prod, S, gps, gj, st)) != cudaSuccess) return fail_cuda(e, "bwd_prep");
+
+    BwdRowArgs ra;
+    ra.zs = zs; ra.ns = ns; ra.qmax = qmax; ra.gps = gps; ra.gj = gj; ra.J2 = J2; ra.mu_pad = mu_pad;
+    ra.s2 = s2; ra.ld_s2 = p.ld_s2; ra.Apart = Apart; ra.CRpart = CRpart;
+    ra.b_loc = b_loc; ra.bl_pad = p.bl_pad; ra.bg_pad = p.bg_pad; ra.row_offset = row_offset; ra.js_len = p.js_len_bwr; ra.w = w;
+    if ((e = launch_bwd_row(p, ra, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_row");
+
+    BwdColArgs ca;
+    ca.zs = zs; ca.ns = ns; ca.qmax = qmax; ca.gps = gps; ca.gj = gj; ca.J2 = J2; ca.mu_pad = mu_pad;
+    ca.s2 = s2; ca.ld_s2 = p.ld_s2; ca.Gpart = Gpart;
+    ca.b_loc = b_loc; ca.bl_pad = p.bl_pad; ca.bg_pad = p.bg_pad; ca.row_offset = row_offset; ca.is_len = p.is_len; ca.w = w;
+    if ((e = launch_bwd_col(p, ca, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_col");
+
+    BwdFinArgs fa;
+    fa.Apart = Apart; fa.CRpart = CRpart; fa.Gpart = Gpart; fa.ns = ns; fa.vr = vr;
+    fa.grad_z = grad_z; fa.ldgz = ldgz; fa.grad_lv = grad_logvar; fa.ldglv = ldglv; fa.grad_mu = grad_mu_all; fa.ldgmu = ldgmu;
+    fa.b_loc = b_loc; fa.b_glob = b_glob; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.d = d; fa.dp = p.dp;
+    fa.n_js = p.n_js_bwr; fa.n_is = p.n_is;
+    if ((e = launch_bwd_finalize(p, fa, st)) != cudaSuccess) return fail_cuda(e, "bwd_finalize");
+    return TCELBO_OK;
+}
+
+#define ROWOP_CHECK(cond, msg) do { if (!(cond)) return fail(TCELBO_ERR_INVALID, msg); } while (0)
+
+int tcelbo_kl_forward(const float* logvar, int64_t ldlv, const float* mu, int64_t ldmu, int b, int d, float* kl_rows, void* stream) {
+    ROWOP_CHECK(logvar && mu && kl_rows, "null pointer");
+    ROWOP_CHECK(b >= 1 && d >= 1 && ldlv >= d && ldmu >= d, "bad shape");
+    cudaError_t e = launch_kl_fwd(logvar, ldlv, mu, ldmu, b, d, kl_rows, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "kl_fwd");
+}
+
+int tcelbo_kl_backward(const float* logvar, int64_t ldlv, const float* mu, int64_t ldmu, const float* g_rows, int b, int d,
+                       float* grad_logvar, int64_t ldglv, float* grad_mu, int64_t ldgmu, void* stream) {
+    ROWOP_CHECK(logvar && mu && g_rows && grad_logvar && grad_mu, "null pointer");
+    ROWOP_CHECK(b >= 1 && d >= 1 && ldlv >= d && ldmu >= d && ldglv >= d && ldgmu >= d, "bad shape");
+    cudaError_t e = launch_kl_bwd(logvar, ldlv, mu, ldmu, g_rows, b, d, grad_logvar, ldglv, grad_mu, ldgmu, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "kl_bwd");
+}
+
+int tcelbo_reparam_forward(const float* mu, int64_t ldmu, const float* logvar, int64_t ldlv, const float* eps, int64_t ldeps,
+                           int b, int d, float* z, int64_t ldz, void* stream) {
+    ROWOP_CHECK(mu && logvar && eps && z, "null pointer");
+    ROWOP_CHECK(b >= 1 && d >= 1 && ldmu >= d && ldlv >= d && ldeps >= d && ldz >= d, "bad shape");
+    cudaError_t e = launch_reparam_fwd(mu, ldmu, logvar, ldlv, eps, ldeps, b, d, z, ldz, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "reparam_fwd");
+}
+
+int tcelbo_reparam_backward(const float* logvar, int64_t ldlv, const float* eps, int64_t ldeps, const float* g_z, int64_t ldgz,
+                            int b, int d, float* grad_mu, int64_t ldgmu, float* grad_logvar, int64_t ldglv, void* stream) {
+    ROWOP_CHECK(logvar && eps && g_z && grad_mu && grad_logvar, "null pointer");
+    ROWOP_CHECK(b >= 1 && d >= 1 && ldlv >= d && ldeps >= d && ldgz >= d && ldgmu >= d && ldglv >= d, "bad shape");
+    cudaError_t e = launch_reparam_bwd(logvar, ldlv, eps, ldeps, g_z, ldgz, b, d, grad_mu, ldgmu, grad_logvar, ldglv, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "reparam_bwd");
+}
+
+int tcelbo_rowdensity_forward(const float* x, int64_t ldx, const float* mu, int64_t ldmu, const float* logvar, int64_t ldlv,
+                              int b, int d, float* out, void* stream) {
+    ROWOP_CHECK(x && out, "null pointer");
+    ROWOP_CHECK(b >= 1 && d >= 1 && ldx >= d && (!mu || ldmu >= d) && (!logvar || ldlv >= d), "bad shape");
+    cudaError_t e = launch_rowdensity_fwd(x, ldx, mu, ldmu, logvar, ldlv, b, d, out, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "rowdensity_fwd");
+}
+
+int tcelbo_rowdensity_backward(const float* x, int64_t ldx, const float* mu, int64_t ldmu, const float* logvar, int64_t ldlv,
+                               const float* g_rows, int b, int d, float* grad_x, int64_t ldgx, float* grad_mu, int64_t ldgmu,
+                               float* grad_logvar, int64_t ldglv, void* stream) {
+    ROWOP_CHECK(x && g_rows, "null pointer");
+    ROWOP_CHECK(b >= 1 && d >= 1 && ldx >= d && (!mu || ldmu >= d) && (!logvar || ldlv >= d), "bad shape");
+    ROWOP_CHECK((!grad_x || ldgx >= d) && (!grad_mu || ldgmu >= d) && (!grad_logvar || ldglv >= d), "bad gradient pitch");
+    cudaError_t e = launch_rowdensity_bwd(x, ldx, mu, ldmu, logvar, ldlv, g_rows, b, d, grad_x, ldgx, grad_mu, ldgmu,
+                                          grad_logvar, ldglv, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "rowdensity_bwd");
+}
+
+long long tcelbo_launch_count(void) { return instr().launches.load(); }
+
+int tcelbo_profile_events(int kernel_id, void* start_event, void* stop_event) {
+    if (kernel_id < 0 || kernel_id > 3) return fail(TCELBO_ERR_INVALID, "kernel_id must be 0..3");
+    Instr& in = instr();
+    in.timed_kernel = kernel_id;
+    in.ev_start = static_cast<cudaEvent_t>(start_event);
+    in.ev_stop = static_cast<cudaEvent_t>(stop_event);
+    return TCELBO_OK;
+}
+
+int tcelbo_ex2_peak(float* scratch, int iters, int ctas, void* stream) {
+    ROWOP_CHECK(scratch && iters > 0 && ctas > 0, "bad argument");
+    cudaError_t e = launch_ex2_peak(scratch, iters, ctas, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "ex2_peak");
+}
+
+}  // extern "C"

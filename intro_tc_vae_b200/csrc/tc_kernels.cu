@@ -1,0 +1,750 @@
+// TC-ELBO kernels for sm_100a: the B x B x D Gaussian log-density matrix of
+// ops.py:80-84 (total_correlation -> gaussian_log_density_torch -> minibatch_stratified_sampling),
+// evaluated tile by tile and reduced on the fly, forward and backward, without ever storing it.
+//
+// Row-variance ("active") variant, ops.py:15-21 with logvar.unsqueeze(1) (ops.py:80-82):
+//   per (i,d)   s = sqrt(0.5*log2e/vc), zs = z*s, ns = -s, qmax = max(0,(50+c)*log2e), shift = max(c,-50)
+//   per (i,j,d) dl = zs + ns*mu_j ; q = dl^2 ; qc = min(q,qmax) ; e = 2^-qc        (lp = shift - ln2*qc)
+//   S_id = sum_j rho_ij e ; s2_ij = sum_d qc ; J2_i = log2 sum_j rho_ij 2^(-s2_ij)
+// rho_ij = w_ij / w_uniform is 1 except in columns 0 and 1 (ops.py:42-49).
+//
+// Layout: columns (mu) are staged through shared memory by 1-D bulk TMA (cp.async.bulk + mbarrier,
+// 3 stages); rows live in registers for the whole sweep.  See DESIGN.md for the thread mappings.
+#include "tc_common.cuh"
+#include "tc_kernels.h"
+#include "tc_instr.h"
+
+namespace tcelbo {
+
+// =====================================================================================================
+// Prologues: pad/copy the column operand, derive the per-(i,d) constants
+// =====================================================================================================
+__global__ void col_prep_kernel(const float* __restrict__ mu_all, int64_t ldmu, int b_glob, int d,
+                                int bg_pad, int dp, float* __restrict__ mu_pad) {
+    const int64_t n = (int64_t)bg_pad * dp;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / dp), dd = (int)(idx % dp);
+        mu_pad[idx] = (j < b_glob && dd < d) ? mu_all[(int64_t)j * ldmu + dd] : 0.0f;
+    }
+}
+
+__global__ void row_prep_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ logvar, int64_t ldlv,
+                                int b_loc, int d, int bl_pad, int dp,
+                                float* __restrict__ zs, float* __restrict__ ns, float* __restrict__ qmax,
+                                float* __restrict__ shift, float* __restrict__ vr) {
+    const int64_t n = (int64_t)bl_pad * dp;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / dp), dd = (int)(idx % dp);
+        float o_zs = 0.f, o_ns = 0.f, o_q = 0.f, o_sh = 0.f, o_vr = 0.f;
+        if (i < b_loc && dd < d) {
+            const float lv = logvar[(int64_t)i * ldlv + dd];
+            const float zv = z[(int64_t)i * ldz + dd];
+            const float var = expf(lv);
+            const float vc = (var < kVarFloor) ? kVarFloor : var;       // NaN stays NaN, like clamp_
+            const float iv = 1.0f / vc;
+            const float c = -0.5f * (logf(vc) + kLog2Pi);
+            const float s = sqrtf(0.5f * kLog2e * iv);
+            o_zs = zv * s;
+            o_ns = -s;
+            o_q = fmaxf(0.0f, (50.0f + c) * kLog2e);
+            o_sh = (c < kLogpFloor) ? kLogpFloor : c;
+            o_vr = 0.5f * var * iv;                                     // straight-through floor: d/dlv uses the unclamped var
+        }
+        zs[idx] = o_zs; ns[idx] = o_ns; qmax[idx] = o_q; shift[idx] = o_sh; vr[idx] = o_vr;
+    }
+}
+
+// =====================================================================================================
+// Forward sweep.  LPR lanes share one row (each lane owns 32 of the row's dims: 16-byte chunks
+// {l + LPR*k}, k = 0..7), so a warp covers 32/LPR rows and the d-sum of a pair (i,j) needs only
+// log2(LPR) shuffles.  grid = (row blocks, column splits); partial results go to the workspace.
+// =====================================================================================================
+template <int LPR, bool kWeighted>
+__device__ __forceinline__ float fwd_one_column(const float* __restrict__ mu_row,   // smem row of column j, + 4*l
+                                                 const u64 (&zs2)[16], const u64 (&ns2)[16], const float (&qmx)[32],
+                                                 u64 (&S2)[16], float rho) {
+    u64 acc0 = 0ull, acc1 = 0ull;
+    const u64 rho2 = pack2(rho, rho);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 m = *reinterpret_cast<const float4*>(mu_row + 4 * LPR * k);
+        const u64 d01 = ffma2(pack2(m.x, m.y), ns2[2 * k], zs2[2 * k]);
+        const u64 d23 = ffma2(pack2(m.z, m.w), ns2[2 * k + 1], zs2[2 * k + 1]);
+        const u64 q01 = fmul2(d01, d01);
+        const u64 q23 = fmul2(d23, d23);
+        float q0, q1, q2, q3;
+        unpack2(q01, q0, q1); unpack2(q23, q2, q3);
+        q0 = fmin_nan(q0, qmx[4 * k + 0]); q1 = fmin_nan(q1, qmx[4 * k + 1]);
+        q2 = fmin_nan(q2, qmx[4 * k + 2]); q3 = fmin_nan(q3, qmx[4 * k + 3]);
+        u64 e01 = pack2(ex2(-q0), ex2(-q1));
+        u64 e23 = pack2(ex2(-q2), ex2(-q3));
+        if (kWeighted) { e01 = fmul2(e01, rho2); e23 = fmul2(e23, rho2); }
+        S2[2 * k] = fadd2(S2[2 * k], e01);
+        S2[2 * k + 1] = fadd2(S2[2 * k + 1], e23);
+        acc0 = fadd2(acc0, pack2(q0, q1));
+        acc1 = fadd2(acc1, pack2(q2, q3));
+    }
+    acc0 = fadd2(acc0, acc1);
+    float a, b; unpack2(acc0, a, b);
+    return a + b;
+}
+
+template <int LPR, bool kSpecial>
+__device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt, int jt0, int l, int i_glob, bool row_store,
+                                         const Weights& w, const u64 (&zs2)[16], const u64 (&ns2)[16], const float (&qmx)[32],
+                                         u64 (&S2)[16], float& lse_m, float& lse_s, float* __restrict__ s2_row) {
+    constexpr int DP = 32 * LPR;
+    constexpr int G = LPR < 4 ? LPR : 4;
+    for (int jj = 0; jj < jt; jj += 4) {
+        float part[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float rho = 1.0f, l2 = 0.0f;
+            if (kSpecial) weight_of(w, i_glob, jt0 + jj + u, rho, l2);
+            part[u] = fwd_one_column<LPR, kSpecial>(tile + (jj + u) * DP + 4 * l, zs2, ns2, qmx, S2, rho);
+        }
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+        }
+        if (LPR >= 4) {
+            const int u = l & 3;
+            const float mine = (u == 0) ? part[0] : (u == 1) ? part[1] : (u == 2) ? part[2] : part[3];
+            const int j = jt0 + jj + u;
+            float x = -mine;
+            if (kSpecial) { float rho, l2; weight_of(w, i_glob, j, rho, l2); x += l2; }
+            lse2_push(lse_m, lse_s, x);
+            if (s2_row != nullptr && row_store && l < 4) s2_row[j] = mine;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if ((u & (G - 1)) == (l & (G - 1))) {
+                    const int j = jt0 + jj + u;
+                    float x = -part[u];
+                    if (kSpecial) { float rho, l2; weight_of(w, i_glob, j, rho, l2); x += l2; }
+                    lse2_push(lse_m, lse_s, x);
+                    if (s2_row != nullptr && row_store) s2_row[j] = part[u];
+                }
+            }
+        }
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(kFwdWarps * 32, 3)
+tc_fwd_kernel(const FwdArgs a) {
+    constexpr int DP = 32 * LPR;
+    constexpr int RPW = 32 / LPR;
+    constexpr int ROWS = kFwdWarps * RPW;
+    constexpr int JT = (kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP);
+    constexpr int TILE = JT * DP;
+    constexpr int G = LPR < 4 ? LPR : 4;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);                       // [kStages][TILE]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * TILE * sizeof(float));
+    uint64_t* bar_empty = bar_full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l = lane % LPR, rw = lane / LPR;
+    const int row = blockIdx.x * ROWS + warp * RPW + rw;                     // < bl_pad by construction
+    const int i_glob = a.row_offset + row;
+    const bool row_valid = true;   // padded rows hold finite zeros: store their s2 too so backward never reads garbage
+
+    // ---- this thread's slice of the row constants -> registers
+    u64 zs2[16], ns2[16], S2[16];
+    float qmx[32];
+    {
+        const float* pz = a.zs + (size_t)row * DP + 4 * l;
+        const float* pn = a.ns + (size_t)row * DP + 4 * l;
+        const float* pq = a.qmax + (size_t)row * DP + 4 * l;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 vz = __ldg(reinterpret_cast<const float4*>(pz + 4 * LPR * k));
+            const float4 vn = __ldg(reinterpret_cast<const float4*>(pn + 4 * LPR * k));
+            const float4 vq = __ldg(reinterpret_cast<const float4*>(pq + 4 * LPR * k));
+            zs2[2 * k] = pack2(vz.x, vz.y); zs2[2 * k + 1] = pack2(vz.z, vz.w);
+            ns2[2 * k] = pack2(vn.x, vn.y); ns2[2 * k + 1] = pack2(vn.z, vn.w);
+            qmx[4 * k] = vq.x; qmx[4 * k + 1] = vq.y; qmx[4 * k + 2] = vq.z; qmx[4 * k + 3] = vq.w;
+            S2[2 * k] = 0ull; S2[2 * k + 1] = 0ull;
+        }
+    }
+    float lse_m = kNegBig, lse_s = 0.0f;
+
+    const int j0 = blockIdx.y * a.js_len;
+    const int j1 = min(a.bg_pad, j0 + a.js_len);
+    const int ntiles = (j1 - j0) / JT;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kFwdWarps); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && ntiles > 0) {
+        mbar_arrive_expect_tx(&bar_full[0], TILE * sizeof(float));
+        bulk_g2s(tiles, a.mu_pad + (size_t)j0 * DP, TILE * sizeof(float), &bar_full[0]);
+    }
+
+    float* s2_row = (a.s2 != nullptr) ? a.s2 + (size_t)row * a.ld_s2 : nullptr;
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int st = t % kStages;
+        if (threadIdx.x == 0 && t + 1 < ntiles) {                              // prefetch tile t+1
+            const int sn = (t + 1) % kStages;
+            if (t + 1 >= kStages) mbar_wait(&bar_empty[sn], (((t + 1) / kStages) - 1) & 1);
+            mbar_arrive_expect_tx(&bar_full[sn], TILE * sizeof(float));
+            bulk_g2s(tiles + (size_t)sn * TILE, a.mu_pad + (size_t)(j0 + (t + 1) * JT) * DP, TILE * sizeof(float), &bar_full[sn]);
+        }
+        mbar_wait(&bar_full[st], (t / kStages) & 1);
+        const float* tile = tiles + (size_t)st * TILE;
+        const int jt0 = j0 + t * JT;
+        const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
+        if (special) fwd_tile<LPR, true>(tile, JT, jt0, l, i_glob, row_valid, a.w, zs2, ns2, qmx, S2, lse_m, lse_s, s2_row);
+        else         fwd_tile<LPR, false>(tile, JT, jt0, l, i_glob, row_valid, a.w, zs2, ns2, qmx, S2, lse_m, lse_s, s2_row);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[st]);
+    }
+
+    // ---- partial results of this (row block, column split)
+    {
+        float* ps = a.Spart + ((size_t)blockIdx.y * a.bl_pad + row) * DP + 4 * l;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float4 v;
+            unpack2(S2[2 * k], v.x, v.y); unpack2(S2[2 * k + 1], v.z, v.w);
+            *reinterpret_cast<float4*>(ps + 4 * LPR * k) = v;
+        }
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, lse_m, o);
+            const float s2v = __shfl_xor_sync(0xffffffffu, lse_s, o);
+            lse2_merge(lse_m, lse_s, m2, s2v);
+        }
+        if (l == 0) {
+            float2* pj = reinterpret_cast<float2*>(a.Jpart) + (size_t)blockIdx.y * a.bl_pad + row;
+            *pj = make_float2(lse_m, lse_s);
+        }
+    }
+}
+
+// one warp per row: sum the column-split partials, take logs, emit log_qz / log_qz_prod
+__global__ void fwd_finalize_kernel(const FinArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= a.b_loc) return;
+    float P = 0.0f, C = 0.0f;
+    for (int dd = lane; dd < a.dp; dd += 32) {
+        float S = 0.0f;
+        for (int s = 0; s < a.n_js; ++s) S += a.Spart[((size_t)s * a.bl_pad + row) * a.dp + dd];
+        a.S[(size_t)row * a.dp + dd] = S;
+        if (dd < a.d) {
+            const float sh = a.shift[(size_t)row * a.dp + dd];
+            P += (logf(S) + a.lw_u) + sh;
+            C += sh;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        P += __shfl_xor_sync(0xffffffffu, P, o);
+        C += __shfl_xor_sync(0xffffffffu, C, o);
+    }
+    if (lane == 0) {
+        const float2* pj = reinterpret_cast<const float2*>(a.Jpart);
+        float m = kNegBig, s = 0.0f;
+        for (int k = 0; k < a.n_js; ++k) {
+            const float2 v = pj[(size_t)k * a.bl_pad + row];
+            const float mn = fmaxf(m, v.x);
+            s = s * exp2f(m - mn) + v.y * exp2f(v.x - mn);
+            m = mn;
+        }
+        const float J2 = m + log2f(s);
+        a.J2[row] = J2;
+        a.log_qz[row] = kLn2 * J2 + C + a.lw_u;
+        a.log_qz_prod[row] = P;
+    }
+}
+
+// =====================================================================================================
+// Backward.  r_ijd = (gJ_i q_ij + gP_i p_ijd) m_ijd with p = rho e / S, q_ij = rho 2^(-s2_ij - J2_i),
+// m = [q <= qmax] (gradient mask of the -50 clamp).  Two sweeps recompute e:
+//   row pass   (rows in registers, columns streamed): A_id = sum_j r dl,  CR_id = sum_j r (2 ln2 q - 1)
+//   column pass(columns in registers, rows streamed): G_jd = sum_i r dl ns_id
+// Thread mapping for both: the 32 lanes of a warp span the latent dims (VEC consecutive dims per lane
+// and chunk), so accumulators never cross lanes and no shuffles are needed.
+// =====================================================================================================
+__global__ void bwd_prep_kernel(const float* __restrict__ g_log_qz, const float* __restrict__ g_log_qz_prod,
+                                const float* __restrict__ S, int b_loc, int bl_pad, int dp,
+                                float* __restrict__ gps, float* __restrict__ gj) {
+    const int64_t n = (int64_t)bl_pad * dp;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / dp);
+        gps[idx] = (i < b_loc) ? g_log_qz_prod[i] / S[idx] : 0.0f;
+        if (idx < bl_pad) gj[idx] = (idx < b_loc) ? g_log_qz[idx] : 0.0f;
+    }
+}
+
+template <int VEC> struct VecLoad;
+template <> struct VecLoad<1> { static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) { v[0] = *p; } };
+template <> struct VecLoad<2> { static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) {
+    const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; } };
+template <> struct VecLoad<4> { static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
+
+// element update shared by both backward sweeps; returns r (masked coefficient) and dl
+template <bool kWeighted>
+__device__ __forceinline__ void bwd_element(float mu, float zs, float ns, float qmx, float gps, float gq, float rho,
+                                            float& r, float& dl, float& qc) {
+    dl = fmaf(mu, ns, zs);
+    const float q = dl * dl;
+    qc = fmin_nan(q, qmx);
+    float e = ex2(-qc);
+    if (kWeighted) e *= rho;
+    const float coef = fmaf(e, gps, gq);
+    r = (q > qmx) ? 0.0f : coef;
+}
+
+template <int DPT, int RI>
+__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+tc_bwd_row_kernel(const BwdRowArgs a) {
+    constexpr int VEC = DPT < 4 ? DPT : 4;
+    constexpr int NCH = DPT / VEC;
+    constexpr int DP = 32 * DPT;
+    constexpr int CH = 32 * VEC;                                             // dims per chunk
+    constexpr int JT = (kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP);
+    constexpr int TILE = JT * DP;
+    constexpr int ROWS = kBwdWarps * RI;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* mu_tiles = reinterpret_cast<float*>(smem_raw);                    // [kStages][TILE]
+    float* s2_tiles = mu_tiles + (size_t)kStages * TILE;                     // [kStages][ROWS][JT]
+    float* gq_buf = s2_tiles + (size_t)kStages * ROWS * JT;                  // [kBwdWarps][RI][JT]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gq_buf + (size_t)kBwdWarps * RI * JT);
+    uint64_t* bar_empty = bar_full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * ROWS + warp * RI;                          // first of this warp's RI rows
+
+    float zs[RI][DPT], ns[RI][DPT], qmx[RI][DPT], gps[RI][DPT], A[RI][DPT], CR[RI][DPT];
+    float gJ[RI], J2[RI];
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+        const size_t base = (size_t)(row0 + r) * DP;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            float v[VEC];
+            VecLoad<VEC>::ld(a.zs + base + c * CH + VEC * lane, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) zs[r][c * VEC + e] = v[e];
+            VecLoad<VEC>::ld(a.ns + base + c * CH + VEC * lane, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) ns[r][c * VEC + e] = v[e];
+            VecLoad<VEC>::ld(a.qmax + base + c * CH + VEC * lane, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) qmx[r][c * VEC + e] = v[e];
+            VecLoad<VEC>::ld(a.gps + base + c * CH + VEC * lane, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) gps[r][c * VEC + e] = v[e];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { A[r][c * VEC + e] = 0.0f; CR[r][c * VEC + e] = 0.0f; }
+        }
+        gJ[r] = a.gj[row0 + r];
+        J2[r] = a.J2[row0 + r];
+    }
+
+    const int j0 = blockIdx.y * a.js_len;
+    const int j1 = min(a.bg_pad, j0 + a.js_len);
+    const int ntiles = (j1 - j0) / JT;
+    constexpr uint32_t kTxBytes = (TILE + ROWS * JT) * sizeof(float);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kBwdWarps); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {                                                // warp 0, all lanes
+        const int sn = t % kStages;
+        if (lane == 0) {
+            if (t >= kStages) mbar_wait(&bar_empty[sn], ((t / kStages) - 1) & 1);
+            mbar_arrive_expect_tx(&bar_full[sn], kTxBytes);
+            bulk_g2s(mu_tiles + (size_t)sn * TILE, a.mu_pad + (size_t)(j0 + t * JT) * DP, TILE * sizeof(float), &bar_full[sn]);
+        }
+        __syncwarp();
+        for (int r = lane; r < ROWS; r += 32)
+            bulk_g2s(s2_tiles + ((size_t)sn * ROWS + r) * JT,
+                     a.s2 + (size_t)(blockIdx.x * ROWS + r) * a.ld_s2 + (j0 + t * JT), JT * sizeof(float), &bar_full[sn]);
+    };
+    if (warp == 0 && ntiles > 0) issue(0);
+
+    float* gq = gq_buf + (size_t)warp * RI * JT;
+    for (int t = 0; t < ntiles; ++t) {
+        const int st = t % kStages;
+        if (warp == 0 && t + 1 < ntiles) issue(t + 1);
+        mbar_wait(&bar_full[st], (t / kStages) & 1);
+        const float* tile = mu_tiles + (size_t)st * TILE;
+        const float* s2t = s2_tiles + ((size_t)st * ROWS + warp * RI) * JT;
+        const int jt0 = j0 + t * JT;
+        const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
+
+        // joint-term coefficients gJ_i * q_ij of this warp's rows for the tile (4 per lane)
+        __syncwarp();
+        for (int idx = lane; idx < RI * JT; idx += 32) {
+            const int r = idx / JT, jj = idx % JT;
+            float rho = 1.0f, l2 = 0.0f;
+            if (special) weight_of(a.w, a.row_offset + row0 + r, jt0 + jj, rho, l2);
+            float gjr = gJ[0], j2r = J2[0];
+#pragma unroll
+            for (int rr = 1; rr < RI; ++rr) if (r == rr) { gjr = gJ[rr]; j2r = J2[rr]; }
+            const float qv = ex2(l2 - s2t[idx] - j2r);
+            gq[idx] = (jt0 + jj < a.w.b_glob) ? gjr * qv : 0.0f;
+        }
+        __syncwarp();
+
+        for (int jj = 0; jj < JT; jj += 4) {
+            float gq4[RI][4];
+#pragma unroll
+            for (int r = 0; r < RI; ++r) {
+                const float4 t4 = *reinterpret_cast<const float4*>(gq + r * JT + jj);
+                gq4[r][0] = t4.x; gq4[r][1] = t4.y; gq4[r][2] = t4.z; gq4[r][3] = t4.w;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float mu[DPT];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    float v[VEC];
+                    VecLoad<VEC>::ld(tile + (jj + u) * DP + c * CH + VEC * lane, v);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) mu[c * VEC + e] = v[e];
+                }
+#pragma unroll
+                for (int r = 0; r < RI; ++r) {
+                    float rho = 1.0f, l2 = 0.0f;
+                    if (special) weight_of(a.w, a.row_offset + row0 + r, jt0 + jj + u, rho, l2);
+#pragma unroll
+                    for (int e = 0; e < DPT; ++e) {
+                        float rr, dl, qc;
+                        if (special) bwd_element<true>(mu[e], zs[r][e], ns[r][e], qmx[r][e], gps[r][e], gq4[r][u], rho, rr, dl, qc);
+                        else         bwd_element<false>(mu[e], zs[r][e], ns[r][e], qmx[r][e], gps[r][e], gq4[r][u], rho, rr, dl, qc);
+                        A[r][e] = fmaf(rr, dl, A[r][e]);
+                        CR[r][e] = fmaf(rr, fmaf(qc, kTwoLn2, -1.0f), CR[r][e]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[st]);
+    }
+
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+        const size_t base = ((size_t)blockIdx.y * a.bl_pad + row0 + r) * DP;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                a.Apart[base + c * CH + VEC * lane + e] = A[r][c * VEC + e];
+                a.CRpart[base + c * CH + VEC * lane + e] = CR[r][c * VEC + e];
+            }
+        }
+    }
+}
+
+template <int DPT, int RJ>
+__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+tc_bwd_col_kernel(const BwdColArgs a) {
+    constexpr int VEC = DPT < 4 ? DPT : 4;
+    constexpr int NCH = DPT / VEC;
+    constexpr int DP = 32 * DPT;
+    constexpr int CH = 32 * VEC;
+    constexpr int IT = (2048 / DP) < 4 ? 4 : ((2048 / DP) > 16 ? 16 : (2048 / DP));
+    constexpr int RT = IT * DP;                                              // floats per row-array tile
+    constexpr int COLS = kBwdWarps * RJ;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* row_tiles = reinterpret_cast<float*>(smem_raw);                   // [kStages][4][RT]  zs, ns, qmax, gps
+    float* s2_tiles = row_tiles + (size_t)kStages * 4 * RT;                  // [kStages][IT][COLS]
+    float* sc_tiles = s2_tiles + (size_t)kStages * IT * COLS;                // [kStages][2][IT]  gJ, J2
+    float* gq_buf = sc_tiles + (size_t)kStages * 2 * IT;                     // [kBwdWarps][IT][RJ]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gq_buf + (size_t)kBwdWarps * IT * RJ);
+    uint64_t* bar_empty = bar_full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col0 = blockIdx.x * COLS + warp * RJ;                          // first of this warp's RJ columns
+
+    float mu[RJ][DPT], G[RJ][DPT];
+#pragma unroll
+    for (int c2 = 0; c2 < RJ; ++c2) {
+        const size_t base = (size_t)(col0 + c2) * DP;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            float v[VEC];
+            VecLoad<VEC>::ld(a.mu_pad + base + c * CH + VEC * lane, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { mu[c2][c * VEC + e] = v[e]; G[c2][c * VEC + e] = 0.0f; }
+        }
+    }
+
+    const int i0 = blockIdx.y * a.is_len;
+    const int i1 = min(a.bl_pad, i0 + a.is_len);
+    const int ntiles = (i1 - i0) / IT;
+    constexpr uint32_t kTxBytes = (4 * RT + IT * COLS + 2 * IT) * sizeof(float);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kBwdWarps); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {                                                // warp 0, all lanes
+        const int sn = t % kStages;
+        const int it0 = i0 + t * IT;
+        if (lane == 0) {
+            if (t >= kStages) mbar_wait(&bar_empty[sn], ((t / kStages) - 1) & 1);
+            mbar_arrive_expect_tx(&bar_full[sn], kTxBytes);
+            float* dst = row_tiles + (size_t)sn * 4 * RT;
+            bulk_g2s(dst + 0 * RT, a.zs + (size_t)it0 * DP, RT * sizeof(float), &bar_full[sn]);
+            bulk_g2s(dst + 1 * RT, a.ns + (size_t)it0 * DP, RT * sizeof(float), &bar_full[sn]);
+            bulk_g2s(dst + 2 * RT, a.qmax + (size_t)it0 * DP, RT * sizeof(float), &bar_full[sn]);
+            bulk_g2s(dst + 3 * RT, a.gps + (size_t)it0 * DP, RT * sizeof(float), &bar_full[sn]);
+            bulk_g2s(sc_tiles + (size_t)sn * 2 * IT, a.gj + it0, IT * sizeof(float), &bar_full[sn]);
+            bulk_g2s(sc_tiles + (size_t)sn * 2 * IT + IT, a.J2 + it0, IT * sizeof(float), &bar_full[sn]);
+        }
+        __syncwarp();
+        for (int r = lane; r < IT; r += 32)
+            bulk_g2s(s2_tiles + ((size_t)sn * IT + r) * COLS,
+                     a.s2 + (size_t)(it0 + r) * a.ld_s2 + blockIdx.x * COLS, COLS * sizeof(float), &bar_full[sn]);
+    };
+    if (warp == 0 && ntiles > 0) issue(0);
+
+    const bool special = a.w.mss && (col0 < 2);                              // this warp owns column 0 and/or 1
+    float* gq = gq_buf + (size_t)warp * IT * RJ;
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int st = t % kStages;
+        if (warp == 0 && t + 1 < ntiles) issue(t + 1);
+        mbar_wait(&bar_full[st], (t / kStages) & 1);
+        const float* rt = row_tiles + (size_t)st * 4 * RT;
+        const float* s2t = s2_tiles + (size_t)st * IT * COLS + warp * RJ;
+        const float* sct = sc_tiles + (size_t)st * 2 * IT;
+        const int it0 = i0 + t * IT;
+
+        __syncwarp();
+        for (int idx = lane; idx < IT * RJ; idx += 32) {
+            const int ii = idx / RJ, c2 = idx % RJ;
+            float rho = 1.0f, l2 = 0.0f;
+            if (special) weight_of(a.w, a.row_offset + it0 + ii, col0 + c2, rho, l2);
+            const float qv = ex2(l2 - s2t[ii * COLS + c2] - sct[IT + ii]);
+            gq[idx] = (col0 + c2 < a.w.b_glob && it0 + ii < a.b_loc) ? sct[ii] * qv : 0.0f;
+        }
+        __syncwarp();
+
+        for (int ii = 0; ii < IT; ++ii) {
+            float zs[DPT], ns[DPT], qmx[DPT], gps[DPT];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float v[VEC];
+                const int off = ii * DP + c * CH + VEC * lane;
+                VecLoad<VEC>::ld(rt + 0 * RT + off, v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) zs[c * VEC + e] = v[e];
+                VecLoad<VEC>::ld(rt + 1 * RT + off, v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) ns[c * VEC + e] = v[e];
+                VecLoad<VEC>::ld(rt + 2 * RT + off, v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) qmx[c * VEC + e] = v[e];
+                VecLoad<VEC>::ld(rt + 3 * RT + off, v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) gps[c * VEC + e] = v[e];
+            }
+            float gqv[RJ];
+#pragma unroll
+            for (int c2 = 0; c2 < RJ; ++c2) gqv[c2] = gq[ii * RJ + c2];
+#pragma unroll
+            for (int c2 = 0; c2 < RJ; ++c2) {
+                float rho = 1.0f, l2 = 0.0f;
+                if (special) weight_of(a.w, a.row_offset + it0 + ii, col0 + c2, rho, l2);
+#pragma unroll
+                for (int e = 0; e < DPT; ++e) {
+                    float rr, dl, qc;
+                    if (special) bwd_element<true>(mu[c2][e], zs[e], ns[e], qmx[e], gps[e], gqv[c2], rho, rr, dl, qc);
+                    else         bwd_element<false>(mu[c2][e], zs[e], ns[e], qmx[e], gps[e], gqv[c2], rho, rr, dl, qc);
+                    G[c2][e] = fmaf(rr * dl, ns[e], G[c2][e]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[st]);
+    }
+
+#pragma unroll
+    for (int c2 = 0; c2 < RJ; ++c2) {
+        const size_t base = ((size_t)blockIdx.y * a.bg_pad + col0 + c2) * DP;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) a.Gpart[base + c * CH + VEC * lane + e] = G[c2][c * VEC + e];
+        }
+    }
+}
+
+__global__ void bwd_finalize_kernel(const BwdFinArgs a) {
+    const int64_t n_row = (int64_t)a.b_loc * a.d;
+    const int64_t n_col = (int64_t)a.b_glob * a.d;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_row + n_col; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (idx < n_row) {
+            const int i = (int)(idx / a.d), dd = (int)(idx % a.d);
+            const size_t o = (size_t)i * a.dp + dd;
+            float sa = 0.0f, sc = 0.0f;
+            for (int s = 0; s < a.n_js; ++s) {
+                sa += a.Apart[(size_t)s * a.bl_pad * a.dp + o];
+                sc += a.CRpart[(size_t)s * a.bl_pad * a.dp + o];
+            }
+            a.grad_z[(int64_t)i * a.ldgz + dd] = kTwoLn2 * a.ns[o] * sa;
+            a.grad_lv[(int64_t)i * a.ldglv + dd] = a.vr[o] * sc;
+        } else {
+            const int64_t k = idx - n_row;
+            const int j = (int)(k / a.d), dd = (int)(k % a.d);
+            const size_t o = (size_t)j * a.dp + dd;
+            float sg = 0.0f;
+            for (int s = 0; s < a.n_is; ++s) sg += a.Gpart[(size_t)s * a.bg_pad * a.dp + o];
+            a.grad_mu[(int64_t)j * a.ldgmu + dd] = -kTwoLn2 * sg;
+        }
+    }
+}
+
+// =====================================================================================================
+// Launchers
+// =====================================================================================================
+static inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
+    int64_t g = (n + block - 1) / block;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+template <int LPR>
+static cudaError_t launch_fwd_t(const Plan& p, const FwdArgs& a, cudaStream_t st) {
+    constexpr int DP = 32 * LPR;
+    constexpr int JT = (kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP);
+    const size_t smem = (size_t)kStages * JT * DP * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    LaunchScope scope(kKernFwd, st);
+    tc_fwd_kernel<LPR><<<dim3(p.n_rb_fwd, p.n_js_fwd), kFwdWarps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_col_prep(const float* mu_all, int64_t ldmu, const Plan& p, float* mu_pad, cudaStream_t st) {
+    const int64_t n = (int64_t)p.bg_pad * p.dp;
+    LaunchScope scope(kKernNone, st);
+    col_prep_kernel<<<grid_for(n, 256), 256, 0, st>>>(mu_all, ldmu, p.b_glob, p.d, p.bg_pad, p.dp, mu_pad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_row_prep(const float* z, int64_t ldz, const float* logvar, int64_t ldlv, const Plan& p,
+                            float* zs, float* ns, float* qmax, float* shift, float* vr, cudaStream_t st) {
+    const int64_t n = (int64_t)p.bl_pad * p.dp;
+    LaunchScope scope(kKernNone, st);
+    row_prep_kernel<<<grid_for(n, 256), 256, 0, st>>>(z, ldz, logvar, ldlv, p.b_loc, p.d, p.bl_pad, p.dp, zs, ns, qmax, shift, vr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st) {
+    switch (p.dpt) {
+        case 1:  return launch_fwd_t<1>(p, a, st);
+        case 2:  return launch_fwd_t<2>(p, a, st);
+        case 4:  return launch_fwd_t<4>(p, a, st);
+        case 8:  return launch_fwd_t<8>(p, a, st);
+        case 16: return launch_fwd_t<16>(p, a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st) {
+    const int warps = 8;
+    LaunchScope scope(kKernNone, st);
+    fwd_finalize_kernel<<<(p.b_loc + warps - 1) / warps, warps * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g_log_qz_prod, const float* S,
+                            float* gps, float* gj, cudaStream_t st) {
+    const int64_t n = (int64_t)p.bl_pad * p.dp;
+    LaunchScope scope(kKernNone, st);
+    bwd_prep_kernel<<<grid_for(n, 256), 256, 0, st>>>(g_log_qz, g_log_qz_prod, S, p.b_loc, p.bl_pad, p.dp, gps, gj);
+    return cudaGetLastError();
+}
+
+template <int DPT, int RI>
+static cudaError_t launch_bwd_row_t(const Plan& p, const BwdRowArgs& a, cudaStream_t st) {
+    constexpr int DP = 32 * DPT;
+    constexpr int JT = (kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP);
+    constexpr int ROWS = kBwdWarps * RI;
+    const size_t smem = ((size_t)kStages * JT * DP + (size_t)kStages * ROWS * JT + (size_t)kBwdWarps * RI * JT) * sizeof(float)
+                        + 2 * kStages * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_bwd_row_kernel<DPT, RI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    LaunchScope scope(kKernBwdRow, st);
+    tc_bwd_row_kernel<DPT, RI><<<dim3(p.n_rb_bwr, p.n_js_bwr), kBwdWarps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bwd_row(const Plan& p, const BwdRowArgs& a, cudaStream_t st) {
+    switch (p.dpt) {
+        case 1:  return launch_bwd_row_t<1, 4>(p, a, st);
+        case 2:  return launch_bwd_row_t<2, 4>(p, a, st);
+        case 4:  return launch_bwd_row_t<4, 4>(p, a, st);
+        case 8:  return launch_bwd_row_t<8, 2>(p, a, st);
+        case 16: return launch_bwd_row_t<16, 1>(p, a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int DPT, int RJ>
+static cudaError_t launch_bwd_col_t(const Plan& p, const BwdColArgs& a, cudaStream_t st) {
+    constexpr int DP = 32 * DPT;
+    constexpr int IT = (2048 / DP) < 4 ? 4 : ((2048 / DP) > 16 ? 16 : (2048 / DP));
+    constexpr int COLS = kBwdWarps * RJ;
+    const size_t smem = ((size_t)kStages * 4 * IT * DP + (size_t)kStages * IT * COLS + (size_t)kStages * 2 * IT
+                         + (size_t)kBwdWarps * IT * RJ) * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_bwd_col_kernel<DPT, RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    LaunchScope scope(kKernBwdCol, st);
+    tc_bwd_col_kernel<DPT, RJ><<<dim3(p.n_cb, p.n_is), kBwdWarps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bwd_col(const Plan& p, const BwdColArgs& a, cudaStream_t st) {
+    switch (p.dpt) {
+        case 1:  return launch_bwd_col_t<1, 8>(p, a, st);
+        case 2:  return launch_bwd_col_t<2, 8>(p, a, st);
+        case 4:  return launch_bwd_col_t<4, 8>(p, a, st);
+        case 8:  return launch_bwd_col_t<8, 4>(p, a, st);
+        case 16: return launch_bwd_col_t<16, 2>(p, a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_bwd_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st) {
+    const int64_t n = (int64_t)p.b_loc * p.d + (int64_t)p.b_glob * p.d;
+    LaunchScope scope(kKernNone, st);
+    bwd_finalize_kernel<<<grid_for(n, 256), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace tcelbo

@@ -1,0 +1,65 @@
+// Kernel argument blocks and launcher prototypes (internal to libtcelbo.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "tc_layout.h"
+#include "tc_common.cuh"
+
+namespace tcelbo {
+
+struct FwdArgs {
+    const float* zs; const float* ns; const float* qmax;   // [bl_pad][dp]
+    const float* mu_pad;                                   // [bg_pad][dp]
+    float* s2; int64_t ld_s2;                              // joint exponents (nullptr: not saved)
+    float* Spart;                                          // [n_js][bl_pad][dp]
+    float* Jpart;                                          // [n_js][bl_pad] (m, s) pairs
+    int b_loc, bl_pad, bg_pad, row_offset, js_len;
+    Weights w;
+};
+
+struct FinArgs {
+    const float* Spart; const float* Jpart; const float* shift;
+    float* S; float* J2; float* log_qz; float* log_qz_prod;
+    int b_loc, bl_pad, d, dp, n_js;
+    float lw_u;
+};
+
+struct BwdRowArgs {
+    const float* zs; const float* ns; const float* qmax; const float* gps;   // [bl_pad][dp]
+    const float* gj; const float* J2;                                        // [bl_pad]
+    const float* mu_pad;                                                     // [bg_pad][dp]
+    const float* s2; int64_t ld_s2;
+    float* Apart; float* CRpart;                                             // [n_js][bl_pad][dp]
+    int b_loc, bl_pad, bg_pad, row_offset, js_len;
+    Weights w;
+};
+
+struct BwdColArgs {
+    const float* zs; const float* ns; const float* qmax; const float* gps;
+    const float* gj; const float* J2;
+    const float* mu_pad;
+    const float* s2; int64_t ld_s2;
+    float* Gpart;                                                            // [n_is][bg_pad][dp]
+    int b_loc, bl_pad, bg_pad, row_offset, is_len;
+    Weights w;
+};
+
+struct BwdFinArgs {
+    const float* Apart; const float* CRpart; const float* Gpart;
+    const float* ns; const float* vr;
+    float* grad_z; int64_t ldgz; float* grad_lv; int64_t ldglv; float* grad_mu; int64_t ldgmu;
+    int b_loc, b_glob, bl_pad, bg_pad, d, dp, n_js, n_is;
+};
+
+cudaError_t launch_col_prep(const float* mu_all, int64_t ldmu, const Plan& p, float* mu_pad, cudaStream_t st);
+cudaError_t launch_row_prep(const float* z, int64_t ldz, const float* logvar, int64_t ldlv, const Plan& p,
+                            float* zs, float* ns, float* qmax, float* shift, float* vr, cudaStream_t st);
+cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st);
+cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st);
+cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g_log_qz_prod, const float* S,
+                            float* gps, float* gj, cudaStream_t st);
+cudaError_t launch_bwd_row(const Plan& p, const BwdRowArgs& a, cudaStream_t st);
+cudaError_t launch_bwd_col(const Plan& p, const BwdColArgs& a, cudaStream_t st);
+cudaError_t launch_bwd_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st);
+
+}  // namespace tcelbo

@@ -1,0 +1,345 @@
+"""Loss helpers of the TC-ELBO path with the reference's call signatures (reference ``ops.py``).
+
+Every function that lies on the hot path runs hand-written sm_100a kernels through the C ABI of
+``libtcelbo.so`` (include/tcelbo.h); inputs must be fp32 CUDA tensors -- there is no CPU or eager
+fallback.  The B x B x D log-density tensor of ops.py:80-82 is never materialised: the fused op
+returns ``(log_qz_prod, log_qz)`` directly and recomputes tiles in backward.
+
+Reference map (file:line in the reference repository):
+    total_correlation            ops.py:52-89
+    tc_terms                     ops.py:80-84 + 104-115 / 92-101 fused (and solvers/tc.py:114-119 for var_of="col")
+    kl_divergence / kl_no_reduce ops.py:136-163   (argument order: logvar, mu)
+    reparameterize               ops.py:166-185
+    log_importance_weight_matrix ops.py:32-49
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .sharding import gather_rows, shard_rows
+
+__all__ = [
+    "total_correlation", "tc_terms", "kl_divergence", "kl_no_reduce", "reparameterize",
+    "log_importance_weight_matrix", "row_log_density",
+]
+
+
+# --------------------------------------------------------------------------------------------------
+# argument plumbing
+# --------------------------------------------------------------------------------------------------
+def _check(name: str, t: Tensor) -> None:
+    if not isinstance(t, Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: the B200 TC-ELBO path only runs on CUDA tensors (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} is {t.dtype}: the B200 TC-ELBO path computes in fp32 only")
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be [batch, latent], got shape {tuple(t.shape)}")
+
+
+def _rows(t: Tensor) -> Tensor:
+    """Row-major with unit inner stride (chunk views with pitch 2*D are passed through untouched)."""
+    if t.stride(1) != 1 or t.stride(0) < t.size(1):
+        t = t.contiguous()
+    return t
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+# --------------------------------------------------------------------------------------------------
+# the fused TC op:  torch.ops.tcelbo.tc_forward / tc_backward
+# --------------------------------------------------------------------------------------------------
+@torch.library.custom_op("tcelbo::tc_forward", mutates_args=(), device_types="cuda")
+def _tc_forward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, dataset_size: int,
+                flags: int) -> Tuple[Tensor, Tensor, Tensor]:
+    lib = _lib.load()
+    z, mu_all, logvar = _rows(z), _rows(mu_all), _rows(logvar)
+    b_loc, d = z.shape
+    b_glob = mu_all.shape[0]
+    nbytes = lib.tcelbo_workspace_bytes(b_loc, b_glob, d, flags)
+    if nbytes == 0:
+        raise NotImplementedError(f"tcelbo: unsupported shape b_loc={b_loc} b_glob={b_glob} d={d} (d must be <= 512)")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+    log_qz = torch.empty(b_loc, dtype=torch.float32, device=z.device)
+    log_qz_prod = torch.empty(b_loc, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        st = lib.tcelbo_forward(z.data_ptr(), z.stride(0), mu_all.data_ptr(), mu_all.stride(0),
+                                logvar.data_ptr(), logvar.stride(0), b_loc, b_glob, row_offset, d, dataset_size, flags,
+                                log_qz.data_ptr(), log_qz_prod.data_ptr(), ws.data_ptr(), nbytes, _stream(z))
+    _lib.check(st, "tcelbo_forward")
+    return log_qz, log_qz_prod, ws
+
+
+@_tc_forward.register_fake
+def _(z, mu_all, logvar, row_offset, dataset_size, flags):
+    nbytes = _lib.load().tcelbo_workspace_bytes(z.shape[0], mu_all.shape[0], z.shape[1], flags)
+    return (z.new_empty(z.shape[0]), z.new_empty(z.shape[0]), z.new_empty(nbytes, dtype=torch.uint8))
+
+
+@torch.library.custom_op("tcelbo::tc_backward", mutates_args=("workspace",), device_types="cuda")
+def _tc_backward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, dataset_size: int, flags: int,
+                 g_log_qz: Tensor, g_log_qz_prod: Tensor, workspace: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    lib = _lib.load()
+    z, mu_all, logvar = _rows(z), _rows(mu_all), _rows(logvar)
+    b_loc, d = z.shape
+    b_glob = mu_all.shape[0]
+    g_log_qz = g_log_qz.contiguous()
+    g_log_qz_prod = g_log_qz_prod.contiguous()
+    grad_z = torch.empty(b_loc, d, dtype=torch.float32, device=z.device)
+    grad_mu = torch.empty(b_glob, d, dtype=torch.float32, device=z.device)
+    grad_lv = torch.empty(logvar.shape[0], d, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        st = lib.tcelbo_backward(z.data_ptr(), z.stride(0), mu_all.data_ptr(), mu_all.stride(0),
+                                 logvar.data_ptr(), logvar.stride(0), b_loc, b_glob, row_offset, d, dataset_size, flags,
+                                 g_log_qz.data_ptr(), g_log_qz_prod.data_ptr(),
+                                 grad_z.data_ptr(), d, grad_mu.data_ptr(), d, grad_lv.data_ptr(), d,
+                                 workspace.data_ptr(), workspace.numel(), _stream(z))
+    _lib.check(st, "tcelbo_backward")
+    return grad_z, grad_mu, grad_lv
+
+
+@_tc_backward.register_fake
+def _(z, mu_all, logvar, row_offset, dataset_size, flags, g_log_qz, g_log_qz_prod, workspace):
+    return (z.new_empty(z.shape), mu_all.new_empty(mu_all.shape), logvar.new_empty(logvar.shape))
+
+
+def _tc_setup_context(ctx, inputs, output):
+    z, mu_all, logvar, row_offset, dataset_size, flags = inputs
+    _, _, ws = output
+    ctx.save_for_backward(z, mu_all, logvar, ws)
+    ctx.meta = (row_offset, dataset_size, flags)
+
+
+def _tc_autograd_backward(ctx, g_log_qz, g_log_qz_prod, _g_ws):
+    z, mu_all, logvar, ws = ctx.saved_tensors
+    row_offset, dataset_size, flags = ctx.meta
+    if not flags & _lib.SAVE_FOR_BACKWARD:
+        raise RuntimeError("tcelbo: forward ran without TCELBO_SAVE_FOR_BACKWARD but a gradient was requested")
+    if g_log_qz is None:
+        g_log_qz = torch.zeros(z.shape[0], dtype=torch.float32, device=z.device)
+    if g_log_qz_prod is None:
+        g_log_qz_prod = torch.zeros(z.shape[0], dtype=torch.float32, device=z.device)
+    gz, gmu, glv = _tc_backward(z, mu_all, logvar, row_offset, dataset_size, flags, g_log_qz, g_log_qz_prod, ws)
+    return gz, gmu, glv, None, None, None
+
+
+_tc_forward.register_autograd(_tc_autograd_backward, setup_context=_tc_setup_context)
+
+
+def tc_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, estimator: str = "mss",
+             var_of: str = "row", group=None) -> Tuple[Tensor, Tensor]:
+    """Fused ``gaussian_log_density* -> minibatch_{stratified,weighted}_sampling``.
+
+    Returns ``(log_qz_prod [B], log_qz [B])`` exactly like ops.py:104-115 / 92-101 applied to the
+    [B,B,D] tensor of ops.py:80-82 (``var_of="row"``) or solvers/tc.py:114-116 (``var_of="col"``).
+
+    ``group``: a torch.distributed process group whose ranks each hold ``B_loc`` consecutive rows of
+    one global batch (rank r owns rows [r*B_loc, (r+1)*B_loc)); ``mu`` (and ``logvar`` for
+    ``var_of="col"``) are all-gathered over NCCL, the weights use global indices, and the backward
+    reduce-scatters the column gradients.  Outputs cover the local rows.
+    """
+    for name, t in (("z", z), ("mu", mu), ("logvar", logvar)):
+        _check(name, t)
+    if not (z.shape == mu.shape == logvar.shape):
+        raise ValueError(f"z, mu, logvar must have one shape, got {tuple(z.shape)}, {tuple(mu.shape)}, {tuple(logvar.shape)}")
+    if estimator not in ("mss", "mws"):
+        raise ValueError(f"estimator must be 'mss' or 'mws', got {estimator!r}")
+    if var_of not in ("row", "col"):
+        raise ValueError(f"var_of must be 'row' or 'col', got {var_of!r}")
+    flags = (_lib.EST_MSS if estimator == "mss" else _lib.EST_MWS) | (_lib.VAR_ROW if var_of == "row" else _lib.VAR_COL)
+    if torch.is_grad_enabled() and (z.requires_grad or mu.requires_grad or logvar.requires_grad):
+        flags |= _lib.SAVE_FOR_BACKWARD
+
+    row_offset = 0
+    mu_all, lv_op = mu, logvar
+    if group is not None:
+        import torch.distributed as dist
+        if dist.get_world_size(group) > 1:
+            row_offset, _ = shard_rows(group, z.shape[0])
+            mu_all = gather_rows(mu, group)
+            if var_of == "col":
+                lv_op = gather_rows(logvar, group)
+    b_glob = mu_all.shape[0]
+    if estimator == "mss" and b_glob == 1:
+        raise ZeroDivisionError("float division by zero")       # ops.py:44 with M = B-1 = 0
+    log_qz, log_qz_prod, _ = _tc_forward(z, mu_all, lv_op, row_offset, int(dataset_size), flags)
+    return log_qz_prod, log_qz
+
+
+def total_correlation(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, reduce: str = "mean",
+                      group=None) -> Tensor:
+    """ops.py:52-89: ``log q(z) - sum_d log q(z_d)`` with minibatch stratified sampling; ``reduce="mean"``
+    returns the batch mean, anything else the per-sample vector."""
+    log_qz_prod, log_qz = tc_terms(z, mu, logvar, dataset_size, "mss", "row", group)
+    tc = log_qz - log_qz_prod
+    return tc.mean() if reduce == "mean" else tc
+
+
+# --------------------------------------------------------------------------------------------------
+# row-wise companions
+# --------------------------------------------------------------------------------------------------
+class _KLRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logvar: Tensor, mu: Tensor) -> Tensor:
+        lib = _lib.load()
+        logvar, mu = _rows(logvar), _rows(mu)
+        b, d = logvar.shape
+        out = torch.empty(b, dtype=torch.float32, device=logvar.device)
+        with torch.cuda.device(logvar.device):
+            st = lib.tcelbo_kl_forward(logvar.data_ptr(), logvar.stride(0), mu.data_ptr(), mu.stride(0), b, d,
+                                       out.data_ptr(), _stream(logvar))
+        _lib.check(st, "tcelbo_kl_forward")
+        ctx.save_for_backward(logvar, mu)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        lib = _lib.load()
+        logvar, mu = ctx.saved_tensors
+        b, d = logvar.shape
+        g = g.contiguous()
+        glv = torch.empty(b, d, dtype=torch.float32, device=logvar.device)
+        gmu = torch.empty(b, d, dtype=torch.float32, device=logvar.device)
+        with torch.cuda.device(logvar.device):
+            st = lib.tcelbo_kl_backward(logvar.data_ptr(), logvar.stride(0), mu.data_ptr(), mu.stride(0), g.data_ptr(),
+                                        b, d, glv.data_ptr(), d, gmu.data_ptr(), d, _stream(logvar))
+        _lib.check(st, "tcelbo_kl_backward")
+        return glv, gmu
+
+
+def kl_no_reduce(logvar: Tensor, mu: Tensor) -> Tensor:
+    """ops.py:161-163: per-sample KL(q(z|x) || N(0, I)) -> [B]."""
+    _check("logvar", logvar)
+    _check("mu", mu)
+    if logvar.shape != mu.shape:
+        raise ValueError("logvar and mu must have one shape")
+    return _KLRows.apply(logvar, mu)
+
+
+def kl_divergence(logvar: Tensor, mu: Tensor, reduce: str = "sum") -> Tensor:
+    """ops.py:136-158.  Argument order is (logvar, mu); ``reduce`` in {"sum", "mean", anything else = none}."""
+    kl = kl_no_reduce(logvar, mu)
+    if reduce == "sum":
+        return kl.sum()
+    if reduce == "mean":
+        return kl.mean()
+    return kl
+
+
+class _Reparam(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu: Tensor, logvar: Tensor, eps: Tensor) -> Tensor:
+        lib = _lib.load()
+        mu, logvar, eps = _rows(mu), _rows(logvar), _rows(eps)
+        b, d = mu.shape
+        z = torch.empty(b, d, dtype=torch.float32, device=mu.device)
+        with torch.cuda.device(mu.device):
+            st = lib.tcelbo_reparam_forward(mu.data_ptr(), mu.stride(0), logvar.data_ptr(), logvar.stride(0),
+                                            eps.data_ptr(), eps.stride(0), b, d, z.data_ptr(), d, _stream(mu))
+        _lib.check(st, "tcelbo_reparam_forward")
+        ctx.save_for_backward(logvar, eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz: Tensor):
+        lib = _lib.load()
+        logvar, eps = ctx.saved_tensors
+        b, d = logvar.shape
+        gz = _rows(gz)
+        gmu = torch.empty(b, d, dtype=torch.float32, device=logvar.device)
+        glv = torch.empty(b, d, dtype=torch.float32, device=logvar.device)
+        with torch.cuda.device(logvar.device):
+            st = lib.tcelbo_reparam_backward(logvar.data_ptr(), logvar.stride(0), eps.data_ptr(), eps.stride(0),
+                                             gz.data_ptr(), gz.stride(0), b, d, gmu.data_ptr(), d, glv.data_ptr(), d,
+                                             _stream(logvar))
+        _lib.check(st, "tcelbo_reparam_backward")
+        return gmu, glv, None
+
+
+def reparameterize(mu: Tensor, logvar: Tensor, eps: Optional[Tensor] = None) -> Tensor:
+    """ops.py:166-185: ``mu + eps * exp(0.5*logvar)``.  ``eps`` defaults to ``torch.randn`` drawn from the
+    device generator exactly as the reference's ``torch.randn_like(std)`` does (same Philox offsets), so
+    seeded runs produce the same samples; pass ``eps`` explicitly for RNG-free use."""
+    _check("mu", mu)
+    _check("logvar", logvar)
+    if eps is None:
+        eps = torch.randn(mu.shape, dtype=torch.float32, device=mu.device)
+    else:
+        _check("eps", eps)
+    return _Reparam.apply(mu, logvar, eps)
+
+
+class _RowDensity(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, mu: Optional[Tensor], logvar: Optional[Tensor]) -> Tensor:
+        lib = _lib.load()
+        x = _rows(x)
+        mu = _rows(mu) if mu is not None else None
+        logvar = _rows(logvar) if logvar is not None else None
+        b, d = x.shape
+        out = torch.empty(b, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            st = lib.tcelbo_rowdensity_forward(x.data_ptr(), x.stride(0),
+                                               mu.data_ptr() if mu is not None else None, mu.stride(0) if mu is not None else 0,
+                                               logvar.data_ptr() if logvar is not None else None,
+                                               logvar.stride(0) if logvar is not None else 0, b, d, out.data_ptr(), _stream(x))
+        _lib.check(st, "tcelbo_rowdensity_forward")
+        ctx.has = (mu is not None, logvar is not None)
+        ctx.save_for_backward(x, *(t for t in (mu, logvar) if t is not None))
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        lib = _lib.load()
+        saved = list(ctx.saved_tensors)
+        x = saved.pop(0)
+        mu = saved.pop(0) if ctx.has[0] else None
+        logvar = saved.pop(0) if ctx.has[1] else None
+        b, d = x.shape
+        g = g.contiguous()
+        gx = torch.empty(b, d, dtype=torch.float32, device=x.device)
+        gmu = torch.empty(b, d, dtype=torch.float32, device=x.device) if mu is not None else None
+        glv = torch.empty(b, d, dtype=torch.float32, device=x.device) if logvar is not None else None
+        with torch.cuda.device(x.device):
+            st = lib.tcelbo_rowdensity_backward(
+                x.data_ptr(), x.stride(0), mu.data_ptr() if mu is not None else None, mu.stride(0) if mu is not None else 0,
+                logvar.data_ptr() if logvar is not None else None, logvar.stride(0) if logvar is not None else 0,
+                g.data_ptr(), b, d, gx.data_ptr(), d, gmu.data_ptr() if gmu is not None else None, d,
+                glv.data_ptr() if glv is not None else None, d, _stream(x))
+        _lib.check(st, "tcelbo_rowdensity_backward")
+        return gx, gmu, glv
+
+
+def row_log_density(x: Tensor, mu: Optional[Tensor] = None, logvar: Optional[Tensor] = None) -> Tensor:
+    """``gaussian_log_density(x, mu, logvar).sum(dim=1)`` (ops.py:24-29, solvers/tc.py:107,112) -> [B].
+    ``mu=None, logvar=None`` is the standard-normal prior log p(z)."""
+    _check("x", x)
+    if mu is not None:
+        _check("mu", mu)
+    if logvar is not None:
+        _check("logvar", logvar)
+    return _RowDensity.apply(x, mu, logvar)
+
+
+# --------------------------------------------------------------------------------------------------
+# host-side helper kept for API parity (the kernels fold the matrix into three scalars)
+# --------------------------------------------------------------------------------------------------
+def log_importance_weight_matrix(batch_size: int, dataset_size: int) -> Tensor:
+    """ops.py:32-49: fp32 [B,B] host tensor; flat stride-B writes hit columns 0 and 1, then W[B-2, 0]."""
+    n = dataset_size
+    m = batch_size - 1
+    strat = (n - m) / (n * m)
+    w = torch.full((batch_size, batch_size), 1.0 / m, dtype=torch.float32)
+    w[:, 0] = 1.0 / n
+    if batch_size > 1:
+        w[:, 1] = strat
+    w[m - 1, 0] = strat
+    return w.log()

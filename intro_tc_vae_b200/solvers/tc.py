@@ -1,0 +1,65 @@
+"""TC loss composition with the reference's solver signatures (reference ``solvers/tc.py:22-144``).
+
+``TCLossMixin`` carries the three methods; ``TCSovler`` (the reference's spelling) binds it to the
+VAE train step.  Only ``self.beta_kl``, ``len(self.dataset)`` and ``self.write_scalar`` are read,
+so the mixin also serves ``IntroTCSovler`` (solvers/intro_tc.py:8-17) and, through
+``intro_tc_vae_b200.install()``, the reference's own solver classes.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+from torch import Tensor
+
+from .. import ops
+from ..utils import SingletonWriter
+from .vae import VAESolver
+
+
+class TCLossMixin:
+    process_group = None          # set to a torch.distributed group to row-shard the estimator
+
+    def compute_kl_loss(self, z: Optional[Tensor], mu: Tensor, logvar: Tensor, reduce: str = "mean",
+                        beta: float = None, write: bool = False) -> Tensor:
+        """solvers/tc.py:58-67: dispatches to the 'simple' form (the only one the reference calls)."""
+        return TCLossMixin._compute_kl_loss_simple(self, z, mu, logvar, reduce, beta, write)
+
+    def _compute_kl_loss_simple(self, z: Optional[Tensor], mu: Tensor, logvar: Tensor, reduce: str = "mean",
+                                beta: float = None, write: bool = False) -> Tensor:
+        """solvers/tc.py:69-89: ``(beta - 1) * TC + KL``; an explicit ``beta=0.0`` is honoured."""
+        if beta is None:
+            beta = self.beta_kl
+        dataset_size = len(self.dataset)
+        kl_loss = ops.kl_divergence(logvar, mu, reduce=reduce)
+        tc = ops.total_correlation(z, mu, logvar, dataset_size, reduce=reduce, group=self.process_group)
+        if write:
+            self.write_scalar(SingletonWriter().cur_iter, "kl_loss_unscaled", kl_loss)   # KL only, as in the reference
+        return (beta - 1.0) * tc + kl_loss
+
+    def _compute_kl_loss_full(self, z: Optional[Tensor], mu: Tensor, logvar: Tensor, reduce: str = "mean",
+                              beta: float = None, write: bool = False) -> Tensor:
+        """solvers/tc.py:91-144: MI + beta * TC + dimension-wise KL, column-variance density, MSS."""
+        if beta is None:
+            beta = self.beta_kl
+        dataset_size = len(self.dataset)
+        logqz_condx = ops.row_log_density(z, mu, logvar)
+        logpz = ops.row_log_density(z)
+        logqz_prodmarginals, log_qz = ops.tc_terms(z, mu, logvar, dataset_size, "mss", "col",
+                                                   getattr(self, "process_group", None))
+        mi_loss = logqz_condx - log_qz
+        tc_loss = log_qz - logqz_prodmarginals
+        kl_loss = logqz_prodmarginals - logpz
+        if reduce == "mean":
+            mi_loss, tc_loss, kl_loss = mi_loss.mean(), tc_loss.mean(), kl_loss.mean()
+            if SingletonWriter().writer:
+                SingletonWriter().writer.add_scalars(
+                    "tc_decomp",
+                    {"mi": mi_loss.data.item(), "tc": tc_loss.data.item(), "kl": kl_loss.data.item()},
+                    global_step=SingletonWriter().cur_iter)
+        if write:
+            self.write_scalar(SingletonWriter().cur_iter, "kl_loss_unscaled", mi_loss + tc_loss + kl_loss)
+        return mi_loss + beta * tc_loss + kl_loss
+
+
+class TCSovler(TCLossMixin, VAESolver):
+    """Same constructor as VAESolver (solvers/tc.py:23-55)."""

@@ -1,0 +1,293 @@
+"""Parity of the CUDA TC-ELBO path (through the C ABI of libtcelbo.so) against
+(a) golden outputs of the live reference (tests/golden), (b) the CPU oracle on seeded inputs,
+(c) size-independent properties at the BASELINE sizes.
+
+Tolerances are the north-star's: 1e-5 relative on every loss term, 1e-4 relative on gradients
+(max-norm relative for vectors: max|a-b| / max|b|).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from cases import CASES, make_inputs
+from oracle import tc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+FINITE_CASES = [c for c in CASES if not c.startswith("nan_")]
+
+
+def _ops():
+    from intro_tc_vae_b200 import ops
+    return ops
+
+
+def relerr(a, b):
+    a = np.asarray(a.detach().cpu() if torch.is_tensor(a) else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if torch.is_tensor(b) else b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _cuda_leafs(case, chunk_view=False):
+    mu_np, lv_np, eps_np = make_inputs(case)
+    dev = torch.device("cuda:0")
+    if chunk_view:      # the encoder's fc output chunked in two: row pitch 2*D (models.py:242-244)
+        y = torch.tensor(np.concatenate([mu_np, lv_np], axis=1), dtype=torch.float32, device=dev, requires_grad=True)
+        mu, lv = y.chunk(2, dim=1)
+        leaf = y
+    else:
+        mu = torch.tensor(mu_np, dtype=torch.float32, device=dev, requires_grad=True)
+        lv = torch.tensor(lv_np, dtype=torch.float32, device=dev, requires_grad=True)
+        leaf = None
+    eps = torch.tensor(eps_np, dtype=torch.float32, device=dev)
+    return mu, lv, eps, leaf
+
+
+@pytest.mark.parametrize("name", FINITE_CASES)
+@pytest.mark.parametrize("chunk_view", [False, True])
+def test_golden_loss_terms_and_grads(golden, name, chunk_view):
+    ops = _ops()
+    case = CASES[name]
+    B, D, N, beta = case["B"], case["D"], case["N"], case["beta"]
+    pre = f"{name}/f32/"
+    mu, lv, eps, leaf = _cuda_leafs(case, chunk_view)
+    z = ops.reparameterize(mu, lv, eps)
+
+    prod, joint = ops.tc_terms(z, mu, lv, N, "mss", "row")
+    assert relerr(prod, golden[pre + "log_qz_prod"]) < LOSS_RTOL
+    assert relerr(joint, golden[pre + "log_qz"]) < LOSS_RTOL
+    tc = ops.total_correlation(z, mu, lv, N, reduce="none")
+    assert relerr(tc, golden[pre + "tc"]) < LOSS_RTOL * max(1.0, np.abs(golden[pre + "log_qz_prod"]).max() / np.abs(golden[pre + "tc"]).max())
+    kl = ops.kl_divergence(lv, mu, reduce="none")
+    assert relerr(kl, golden[pre + "kl"]) < LOSS_RTOL
+    prod_w, joint_w = ops.tc_terms(z, mu, lv, N, "mws", "row")
+    assert relerr(prod_w, golden[pre + "mws_log_qz_prod"]) < LOSS_RTOL
+    assert relerr(joint_w, golden[pre + "mws_log_qz"]) < LOSS_RTOL
+
+    # (beta-1)*tc + kl, mean-reduced, and its gradients through z = mu + eps*std  (solvers/tc.py:69-89)
+    simple = (beta - 1.0) * ops.total_correlation(z, mu, lv, N, reduce="mean") + ops.kl_divergence(lv, mu, reduce="mean")
+    assert abs(simple.item() - float(golden[pre + "simple_mean"])) < LOSS_RTOL * abs(float(golden[pre + "simple_mean"])) * \
+        max(1.0, beta * np.abs(golden[pre + "log_qz_prod"]).mean() / abs(float(golden[pre + "simple_mean"])))
+    gz = torch.autograd.grad(simple, z, retain_graph=True)[0]
+    assert relerr(gz, golden[pre + "simple_mean_dz_partial"]) < GRAD_RTOL
+    simple.backward(retain_graph=True)
+    if chunk_view:
+        gmu, glv = leaf.grad.chunk(2, dim=1)
+        leaf.grad = None
+    else:
+        gmu, glv = mu.grad, lv.grad
+        mu.grad = lv.grad = None
+    assert relerr(gmu, golden[pre + "simple_mean_dmu"]) < GRAD_RTOL
+    assert relerr(glv, golden[pre + "simple_mean_dlv"]) < GRAD_RTOL
+
+    # per-sample loss with an explicit beta and the soft-intro exp-ELBO on top (solvers/intro.py:84-103)
+    simple_none = (beta - 1.0) * ops.total_correlation(z, mu, lv, N, reduce="none") + ops.kl_divergence(lv, mu, reduce="none")
+    ref_none = golden[pre + "simple_none"]
+    assert relerr(simple_none, ref_none) < LOSS_RTOL * max(1.0, beta * np.abs(golden[pre + "log_qz_prod"]).max() / np.abs(ref_none).max())
+    rec_i = torch.arange(B, dtype=torch.float32, device="cuda:0") * 0.3
+    ee = (-2 * (1.0 / (3 * 64 * 64)) * (rec_i + simple_none)).exp().mean()
+    assert abs(ee.item() - float(golden[pre + "expelbo"])) < LOSS_RTOL * abs(float(golden[pre + "expelbo"])) * 10
+    ee.backward()
+    if chunk_view:
+        gmu, glv = leaf.grad.chunk(2, dim=1)
+    else:
+        gmu, glv = mu.grad, lv.grad
+    assert relerr(gmu, golden[pre + "expelbo_dmu"]) < GRAD_RTOL
+    assert relerr(glv, golden[pre + "expelbo_dlv"]) < GRAD_RTOL
+
+
+def test_dataset_smaller_than_batch_is_nan(golden):
+    ops = _ops()
+    case = CASES["nan_B8_D4"]
+    mu, lv, eps, _ = _cuda_leafs(case)
+    z = ops.reparameterize(mu, lv, eps)
+    tc = ops.total_correlation(z, mu, lv, case["N"], reduce="none")
+    assert torch.isnan(tc).all() and np.isnan(golden["nan_B8_D4/f32/tc"]).all()
+
+
+def test_error_conventions():
+    ops = _ops()
+    dev = "cuda:0"
+    one = torch.zeros(1, 8, device=dev)
+    with pytest.raises(ZeroDivisionError):                      # ops.py:44 with B == 1
+        ops.total_correlation(one, one, one, 10)
+    cpu = torch.zeros(4, 8)
+    with pytest.raises(RuntimeError):                           # no CPU fallback
+        ops.total_correlation(cpu, cpu, cpu, 10)
+    dbl = torch.zeros(4, 8, device=dev, dtype=torch.float64)
+    with pytest.raises(TypeError):
+        ops.total_correlation(dbl, dbl, dbl, 10)
+    big = torch.zeros(4, 520, device=dev)
+    with pytest.raises(NotImplementedError):
+        ops.total_correlation(big, big, big, 10)
+
+
+def _random_latents(B, D, family, seed=1234, device="cuda:0"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    if family == "base":          # ~5 % of log-densities clamped
+        mu = torch.randn(B, D, generator=g)
+        lv = -2.0 + torch.randn(B, D, generator=g)
+    else:                         # sharp posteriors: 40-60 % clamped, variance floor active
+        mu = 2.0 * torch.randn(B, D, generator=g)
+        lv = -6.0 + 2.0 * torch.randn(B, D, generator=g)
+    eps = torch.randn(B, D, generator=g)
+    return mu, lv, eps
+
+
+@pytest.mark.parametrize("B,D", [(64, 128), (256, 128), (1024, 128), (96, 32), (80, 64), (48, 256)])
+@pytest.mark.parametrize("family", ["base", "sharp"])
+def test_seeded_inputs_against_cpu_oracle(B, D, family):
+    """Same seeded inputs through the CUDA path and through the fp32 CPU oracle (reference op sequence)."""
+    ops = _ops()
+    N, beta = 16704, 6.0
+    mu_c, lv_c, eps_c = _random_latents(B, D, family)
+    # oracle, fp32 on the CPU
+    mu_o, lv_o = mu_c.clone().requires_grad_(True), lv_c.clone().requires_grad_(True)
+    z_o = O.reparameterize(mu_o, lv_o, eps_c)
+    prod_o, joint_o = O.tc_terms(z_o, mu_o, lv_o, N, "mss", "row")
+    loss_o = O.kl_loss_simple(z_o, mu_o, lv_o, N, beta, "mean")
+    loss_o.backward()
+    # CUDA
+    mu = mu_c.cuda().requires_grad_(True)
+    lv = lv_c.cuda().requires_grad_(True)
+    z = ops.reparameterize(mu, lv, eps_c.cuda())
+    prod, joint = ops.tc_terms(z, mu, lv, N, "mss", "row")
+    loss = (beta - 1.0) * ops.total_correlation(z, mu, lv, N) + ops.kl_divergence(lv, mu, reduce="mean")
+    loss.backward()
+    assert relerr(prod, prod_o) < LOSS_RTOL
+    assert relerr(joint, joint_o) < LOSS_RTOL
+    assert abs(loss.item() - loss_o.item()) < LOSS_RTOL * beta * prod_o.abs().mean().item()
+    assert relerr(mu.grad, mu_o.grad) < GRAD_RTOL
+    assert relerr(lv.grad, lv_o.grad) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("B,D,parts", [(256, 128, 4), (200, 64, 3), (1024, 128, 8)])
+def test_row_sharding_matches_single_shard(B, D, parts):
+    """rank r owns rows [r*B/P, (r+1)*B/P); weights use global indices.  Emulated on one
+    GPU by calling the op per shard with row_offset; outputs concatenate, column gradients add."""
+    from intro_tc_vae_b200 import _lib
+    ops = _ops()
+    N = 16704
+    mu_c, lv_c, eps_c = _random_latents(B, D, "base", seed=7)
+    mu = mu_c.cuda().requires_grad_(True)
+    lv = lv_c.cuda().requires_grad_(True)
+    z = ops.reparameterize(mu, lv, eps_c.cuda()).detach().requires_grad_(True)
+    prod, joint = ops.tc_terms(z, mu, lv, N)
+    w = torch.linspace(0.5, 1.5, B, device="cuda:0")
+    ((joint - prod) * w).sum().backward()
+    full = (prod.detach(), joint.detach(), z.grad.clone(), mu.grad.clone(), lv.grad.clone())
+
+    flags = _lib.EST_MSS | _lib.VAR_ROW | _lib.SAVE_FOR_BACKWARD
+    bounds = [round(k * B / parts) for k in range(parts + 1)]
+    prods, joints, gzs, glvs = [], [], [], []
+    gmu_sum = torch.zeros(B, D, device="cuda:0")
+    for r in range(parts):
+        lo, hi = bounds[r], bounds[r + 1]
+        zr = z.detach()[lo:hi].clone().requires_grad_(True)
+        lvr = lv.detach()[lo:hi].clone().requires_grad_(True)
+        mua = mu.detach().clone().requires_grad_(True)
+        lq, lqp, _ = torch.ops.tcelbo.tc_forward(zr, mua, lvr, lo, N, flags)
+        ((lq - lqp) * w[lo:hi]).sum().backward()
+        prods.append(lqp.detach()); joints.append(lq.detach()); gzs.append(zr.grad); glvs.append(lvr.grad)
+        gmu_sum += mua.grad
+    assert relerr(torch.cat(prods), full[0]) < 1e-6
+    assert relerr(torch.cat(joints), full[1]) < 1e-6
+    assert relerr(torch.cat(gzs), full[2]) < 1e-5
+    assert relerr(gmu_sum, full[3]) < 1e-5
+    assert relerr(torch.cat(glvs), full[4]) < 1e-5
+
+
+def test_column_permutation_invariance_at_full_size():
+    """BASELINE cfg 3 size (B=8192, D=128): log_qz / log_qz_prod of a row do not depend on the order of
+    the uniformly weighted columns j >= 2 (the two stratified columns 0 and 1 stay put), and a handful
+    of rows agree with the row-chunked CPU oracle."""
+    ops = _ops()
+    B, D, N = 8192, 128, 16704
+    mu_c, lv_c, eps_c = _random_latents(B, D, "base", seed=3)
+    z_c = O.reparameterize(mu_c, lv_c, eps_c)
+    mu, lv, z = mu_c.cuda(), lv_c.cuda(), z_c.cuda()
+    prod, joint = ops.tc_terms(z, mu, lv, N)
+    assert torch.isfinite(prod).all() and torch.isfinite(joint).all()
+
+    rows = [0, 1, 2, 4097, B - 2, B - 1]
+    for r in rows:
+        p_o, j_o = O.tc_terms_rows(z_c[r:r + 1], lv_c[r:r + 1], mu_c, r, B, N)
+        assert abs(prod[r].item() - p_o.item()) < LOSS_RTOL * abs(p_o.item())
+        assert abs(joint[r].item() - j_o.item()) < LOSS_RTOL * abs(j_o.item())
+
+    # permute columns >= 2: only mu moves; rows (z, logvar) keep their place, so use the raw op
+    from intro_tc_vae_b200 import _lib
+    perm = torch.cat([torch.arange(2), 2 + torch.randperm(B - 2, generator=torch.Generator().manual_seed(0))]).cuda()
+    lq, lqp, _ = torch.ops.tcelbo.tc_forward(z, mu[perm].contiguous(), lv, 0, N, _lib.EST_MSS | _lib.VAR_ROW)
+    assert relerr(lqp, prod) < 2e-6
+    assert relerr(lq, joint) < 2e-6
+
+
+def test_full_size_gradients_against_chunked_oracle():
+    """B=4096, D=128: gradients of sum_i w_i*tc_i for a few columns/rows against the CPU oracle, which
+    evaluates the needed rows in chunks (rows are independent given all columns)."""
+    ops = _ops()
+    B, D, N = 4096, 128, 16704
+    mu_c, lv_c, eps_c = _random_latents(B, D, "sharp", seed=5)
+    z_c = O.reparameterize(mu_c, lv_c, eps_c)
+    w_c = torch.linspace(0.5, 1.5, B)
+    # oracle: d/d(z_i, lv_i) only needs row i; d/dmu needs all rows -> accumulate over chunks
+    mu_o = mu_c.clone().requires_grad_(True)
+    gz_o = torch.zeros(B, D); glv_o = torch.zeros(B, D)
+    step = 128
+    for r0 in range(0, B, step):
+        zr = z_c[r0:r0 + step].clone().requires_grad_(True)
+        lvr = lv_c[r0:r0 + step].clone().requires_grad_(True)
+        p, j = O.tc_terms_rows(zr, lvr, mu_o, r0, B, N)
+        ((j - p) * w_c[r0:r0 + step]).sum().backward()
+        gz_o[r0:r0 + step] = zr.grad; glv_o[r0:r0 + step] = lvr.grad
+    z = z_c.cuda().requires_grad_(True); mu = mu_c.cuda().requires_grad_(True); lv = lv_c.cuda().requires_grad_(True)
+    prod, joint = ops.tc_terms(z, mu, lv, N)
+    ((joint - prod) * w_c.cuda()).sum().backward()
+    assert relerr(z.grad, gz_o) < GRAD_RTOL
+    assert relerr(lv.grad, glv_o) < GRAD_RTOL
+    assert relerr(mu.grad, mu_o.grad) < GRAD_RTOL
+
+
+def test_rowwise_companions_against_oracle():
+    ops = _ops()
+    B, D = 300, 130
+    mu_c, lv_c, eps_c = _random_latents(B, D, "sharp", seed=11)
+    mu_o, lv_o = mu_c.clone().requires_grad_(True), lv_c.clone().requires_grad_(True)
+    z_o = O.reparameterize(mu_o, lv_o, eps_c)
+    kl_o = O.kl_divergence(lv_o, mu_o, "none")
+    dens_o = O.gaussian_log_density(z_o, mu_o, lv_o).sum(1)
+    prior_o = O.gaussian_log_density(z_o, torch.zeros_like(z_o), torch.zeros_like(z_o)).sum(1)
+    wts = torch.linspace(-1, 2, B)
+    ((kl_o + 0.3 * dens_o - 0.7 * prior_o) * wts).sum().backward()
+
+    mu, lv = mu_c.cuda().requires_grad_(True), lv_c.cuda().requires_grad_(True)
+    z = ops.reparameterize(mu, lv, eps_c.cuda())
+    kl = ops.kl_divergence(lv, mu, reduce="none")
+    dens = ops.row_log_density(z, mu, lv)
+    prior = ops.row_log_density(z)
+    ((kl + 0.3 * dens - 0.7 * prior) * wts.cuda()).sum().backward()
+    assert relerr(z, z_o) < 1e-6
+    assert relerr(kl, kl_o) < LOSS_RTOL
+    assert relerr(dens, dens_o) < LOSS_RTOL
+    assert relerr(prior, prior_o) < LOSS_RTOL
+    assert relerr(mu.grad, mu_o.grad) < GRAD_RTOL
+    assert relerr(lv.grad, lv_o.grad) < GRAD_RTOL
+    assert ops.kl_divergence(lv, mu).dim() == 0 and ops.kl_divergence(lv, mu, reduce="mean").dim() == 0
+
+
+def test_reparameterize_consumes_rng_like_reference():
+    """ops.py:183-185 draws eps with torch.randn_like(std) from the device generator."""
+    ops = _ops()
+    mu = torch.randn(64, 128, device="cuda:0")
+    lv = torch.randn(64, 128, device="cuda:0")
+    torch.manual_seed(123)
+    z = ops.reparameterize(mu, lv)
+    torch.manual_seed(123)
+    std = torch.exp(0.5 * lv)
+    ref = mu + torch.randn_like(std) * std
+    assert relerr(z, ref) < 1e-6
