@@ -24,7 +24,8 @@
  *   - Nothing is allocated, no host synchronisation happens, every call is asynchronous on `stream`
  *     (a cudaStream_t passed as void*) and CUDA-graph capturable.  Scratch comes from the caller:
  *     query tcelbo_workspace_bytes() and pass a 256-byte aligned buffer.  The buffer written by
- *     tcelbo_forward(flags | TCELBO_SAVE_FOR_BACKWARD) must be handed unchanged to tcelbo_backward.
+ *     tcelbo_forward(flags | TCELBO_SAVE_FOR_BACKWARD) must be handed unchanged to tcelbo_backward,
+ *     which only reads it and writes its own scratch (tcelbo_backward_scratch_bytes()).
  *   - Return value: 0 on success, a TCELBO_ERR_* code otherwise; tcelbo_last_error() returns a
  *     thread-local message.  Nothing throws across the boundary.
  *   - Sharding: a rank owns global rows [row_offset, row_offset + b_loc) of a global
@@ -64,8 +65,11 @@ extern "C" {
 int         tcelbo_version(void);
 const char* tcelbo_last_error(void);
 
-/* Bytes of scratch needed by forward (+ backward when TCELBO_SAVE_FOR_BACKWARD is set). */
+/* Bytes of the forward workspace (larger with TCELBO_SAVE_FOR_BACKWARD: it then keeps the per-row results and
+ * the b_loc x b_glob joint exponents that backward reads; never the b x b x d log-densities). */
 size_t tcelbo_workspace_bytes(int b_loc, int b_glob, int d, uint32_t flags);
+/* Bytes of the separate scratch buffer tcelbo_backward writes (the forward workspace is read-only there). */
+size_t tcelbo_backward_scratch_bytes(int b_loc, int b_glob, int d, uint32_t flags);
 
 /*
  * Forward: for each local row i
@@ -99,7 +103,8 @@ int tcelbo_backward(const float* z, int64_t ldz,
                     float* grad_z, int64_t ldgz,
                     float* grad_mu_all, int64_t ldgmu,
                     float* grad_logvar, int64_t ldglv,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    const void* workspace, size_t workspace_bytes,
+                    void* scratch, size_t scratch_bytes, void* stream);
 
 /* kl_rows[i] = -0.5 * sum_d (1 + logvar - exp(logvar) - mu^2)   (ops.py:161-163; argument order logvar, mu) */
 int tcelbo_kl_forward(const float* logvar, int64_t ldlv, const float* mu, int64_t ldmu,

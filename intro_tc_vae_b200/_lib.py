@@ -27,10 +27,12 @@ _SIGNATURES = {
     "tcelbo_version": (c_int, []),
     "tcelbo_last_error": (c_char_p, []),
     "tcelbo_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_uint32]),
+    "tcelbo_backward_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_uint32]),
     "tcelbo_forward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64, c_uint32,
                                _f, _f, c_void_p, c_size_t, c_void_p]),
     "tcelbo_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64, c_uint32,
-                                _f, _f, _f, c_int64, _f, c_int64, _f, c_int64, c_void_p, c_size_t, c_void_p]),
+                                _f, _f, _f, c_int64, _f, c_int64, _f, c_int64, c_void_p, c_size_t, c_void_p, c_size_t,
+                                c_void_p]),
     "tcelbo_kl_forward": (c_int, [_f, c_int64, _f, c_int64, c_int, c_int, _f, c_void_p]),
     "tcelbo_kl_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int, c_int, _f, c_int64, _f, c_int64, c_void_p]),
     "tcelbo_reparam_forward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_int64, c_void_p]),

@@ -105,6 +105,12 @@ size_t tcelbo_workspace_bytes(int b_loc, int b_glob, int d, uint32_t flags) {
     return p.total_bytes;
 }
 
+size_t tcelbo_backward_scratch_bytes(int b_loc, int b_glob, int d, uint32_t flags) {
+    Plan p;
+    if (!make_plan(p, b_loc, b_glob, d, flags, sm_count())) return 0;
+    return p.bwd_bytes;
+}
+
 int tcelbo_forward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
                    int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
                    float* log_qz, float* log_qz_prod, void* workspace, size_t workspace_bytes, void* stream) {
@@ -151,7 +157,7 @@ int tcelbo_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ld
                     int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
                     const float* g_log_qz, const float* g_log_qz_prod,
                     float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
-                    void* workspace, size_t workspace_bytes, void* stream) {
+                    const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream) {
     if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv)) return rc;
     if (!(flags & TCELBO_SAVE_FOR_BACKWARD)) return fail(TCELBO_ERR_INVALID, "backward needs the workspace of a forward run with TCELBO_SAVE_FOR_BACKWARD");
     if (!g_log_qz || !g_log_qz_prod || !grad_z || !grad_mu_all || !grad_logvar) return fail(TCELBO_ERR_INVALID, "null gradient pointer");
@@ -160,23 +166,26 @@ int tcelbo_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ld
     if (!make_plan(p, b_loc, b_glob, d, flags, sm_count())) return fail(TCELBO_ERR_INVALID, "cannot plan this shape");
     if (!workspace || workspace_bytes < p.total_bytes || !aligned256(workspace))
         return fail(TCELBO_ERR_WORKSPACE, "workspace must be the %zu-byte buffer forward wrote (got %zu)", p.total_bytes, workspace_bytes);
+    if (!scratch || scratch_bytes < p.bwd_bytes || !aligned256(scratch))
+        return fail(TCELBO_ERR_WORKSPACE, "scratch must be 256-byte aligned and at least %zu bytes (got %zu)", p.bwd_bytes, scratch_bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Weights w = make_weights(b_glob, dataset_size, flags);
     cudaError_t e;
 
-    const float* mu_pad = at<float>(workspace, p.off_mu);
-    const float* zs = at<float>(workspace, p.off_zs);
-    const float* ns = at<float>(workspace, p.off_ns);
-    const float* qmax = at<float>(workspace, p.off_qmax);
-    const float* vr = at<float>(workspace, p.off_vr);
-    const float* S = at<float>(workspace, p.off_S);
-    const float* J2 = at<float>(workspace, p.off_J2);
-    const float* s2 = at<float>(workspace, p.off_s2);
-    float* gps = at<float>(workspace, p.off_gps);
-    float* gj = at<float>(workspace, p.off_gj);
-    float* Apart = at<float>(workspace, p.off_scratch);
-    float* CRpart = Apart + (size_t)p.n_js_bwr * p.bl_pad * p.dp;
-    float* Gpart = CRpart + (size_t)p.n_js_bwr * p.bl_pad * p.dp;
+    void* wsm = const_cast<void*>(workspace);                       // only read below
+    const float* mu_pad = at<float>(wsm, p.off_mu);
+    const float* zs = at<float>(wsm, p.off_zs);
+    const float* ns = at<float>(wsm, p.off_ns);
+    const float* qmax = at<float>(wsm, p.off_qmax);
+    const float* vr = at<float>(wsm, p.off_vr);
+    const float* S = at<float>(wsm, p.off_S);
+    const float* J2 = at<float>(wsm, p.off_J2);
+    const float* s2 = at<float>(wsm, p.off_s2);
+    float* gps = at<float>(scratch, p.boff_gps);
+    float* gj = at<float>(scratch, p.boff_gj);
+    float* Apart = at<float>(scratch, p.boff_A);
+    float* CRpart = at<float>(scratch, p.boff_CR);
+    float* Gpart = at<float>(scratch, p.boff_G);
 
     if ((e = launch_bwd_prep(p, g_log_qz, g_log_qz_prod, S, gps, gj, st)) != cudaSuccess) return fail_cuda(e, "bwd_prep");
 

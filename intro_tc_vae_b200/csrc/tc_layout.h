@@ -26,10 +26,12 @@ struct Plan {
     int bwc_cols, bwc_rj, bwc_it, n_cb, n_is, is_len;
     // workspace (byte offsets)
     size_t off_mu, off_zs, off_ns, off_qmax, off_shift, off_vr;   // [bg_pad|bl_pad][dp]
-    size_t off_S, off_J2, off_gps, off_gj;                        // persistent forward results
+    size_t off_S, off_J2;                                         // persistent forward results
     size_t off_s2; int64_t ld_s2;                                 // joint exponents [bl_pad][bg_pad]
-    size_t off_scratch;                                           // split partials (fwd: S,J ; bwd: A,CR,G)
-    size_t scratch_bytes, total_bytes;
+    size_t off_scratch;                                           // forward split partials (S, J)
+    size_t total_bytes;                                           // forward workspace (read-only in backward)
+    // backward scratch (its own buffer, so the forward workspace stays immutable and backward can be re-run)
+    size_t boff_gps, boff_gj, boff_A, boff_CR, boff_G, bwd_bytes;
     bool save;
 };
 
@@ -100,15 +102,19 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.off_vr = off;    off = align256(off + row_arr);
     p.off_S = off;     off = align256(off + row_arr);
     p.off_J2 = off;    off = align256(off + (size_t)p.bl_pad * sizeof(float));
-    p.off_gps = off;   off = align256(off + (p.save ? row_arr : 0));
-    p.off_gj = off;    off = align256(off + (p.save ? (size_t)p.bl_pad * sizeof(float) : 0));
     p.ld_s2 = p.bg_pad;
     p.off_s2 = off;    off = align256(off + (p.save ? (size_t)p.bl_pad * p.ld_s2 * sizeof(float) : 0));
     const size_t fwd_scratch = (size_t)p.n_js_fwd * row_arr + (size_t)p.n_js_fwd * p.bl_pad * 2 * sizeof(float);
-    const size_t bwd_scratch = p.save ? (2 * (size_t)p.n_js_bwr * row_arr + (size_t)p.n_is * col_arr) : 0;
-    p.scratch_bytes = fwd_scratch > bwd_scratch ? fwd_scratch : bwd_scratch;
-    p.off_scratch = off; off = align256(off + p.scratch_bytes);
+    p.off_scratch = off; off = align256(off + fwd_scratch);
     p.total_bytes = off;
+
+    size_t b = 0;
+    p.boff_gps = b; b = align256(b + row_arr);
+    p.boff_gj = b;  b = align256(b + (size_t)p.bl_pad * sizeof(float));
+    p.boff_A = b;   b = align256(b + (size_t)p.n_js_bwr * row_arr);
+    p.boff_CR = b;  b = align256(b + (size_t)p.n_js_bwr * row_arr);
+    p.boff_G = b;   b = align256(b + (size_t)p.n_is * col_arr);
+    p.bwd_bytes = b;
     return true;
 }
 

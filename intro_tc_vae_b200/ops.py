@@ -84,7 +84,7 @@ def _(z, mu_all, logvar, row_offset, dataset_size, flags):
     return (z.new_empty(z.shape[0]), z.new_empty(z.shape[0]), z.new_empty(nbytes, dtype=torch.uint8))
 
 
-@torch.library.custom_op("tcelbo::tc_backward", mutates_args=("workspace",), device_types="cuda")
+@torch.library.custom_op("tcelbo::tc_backward", mutates_args=(), device_types="cuda")
 def _tc_backward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, dataset_size: int, flags: int,
                  g_log_qz: Tensor, g_log_qz_prod: Tensor, workspace: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     lib = _lib.load()
@@ -96,12 +96,14 @@ def _tc_backward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, dat
     grad_z = torch.empty(b_loc, d, dtype=torch.float32, device=z.device)
     grad_mu = torch.empty(b_glob, d, dtype=torch.float32, device=z.device)
     grad_lv = torch.empty(logvar.shape[0], d, dtype=torch.float32, device=z.device)
+    nscratch = lib.tcelbo_backward_scratch_bytes(b_loc, b_glob, d, flags)
+    scratch = torch.empty(nscratch, dtype=torch.uint8, device=z.device)
     with torch.cuda.device(z.device):
         st = lib.tcelbo_backward(z.data_ptr(), z.stride(0), mu_all.data_ptr(), mu_all.stride(0),
                                  logvar.data_ptr(), logvar.stride(0), b_loc, b_glob, row_offset, d, dataset_size, flags,
                                  g_log_qz.data_ptr(), g_log_qz_prod.data_ptr(),
                                  grad_z.data_ptr(), d, grad_mu.data_ptr(), d, grad_lv.data_ptr(), d,
-                                 workspace.data_ptr(), workspace.numel(), _stream(z))
+                                 workspace.data_ptr(), workspace.numel(), scratch.data_ptr(), nscratch, _stream(z))
     _lib.check(st, "tcelbo_backward")
     return grad_z, grad_mu, grad_lv
 
