@@ -1,0 +1,338 @@
+// Fused backward sweep of the TC-ELBO estimator (sm_100a): ONE recomputation of e_ijd = 2^-qc per
+// log-density yields all three gradients of ops.py:80-115's autograd graph:
+//     r_ijd  = (gJ_i q_ij + gP_i rho_ij e_ijd / S_id) * [q_ijd <= qmax_id]      (mask of the -50 clamp)
+//     A_id   = sum_j r dl          -> grad_z        (row-local, registers)
+//     CR_id  = sum_j r (2 ln2 qc - 1) -> grad_logvar (row-local, registers)
+//     G_jd   = sum_i r dl ns_id    -> grad_mu       (column sum over rows: warp-partial in registers,
+//                                                     8 warps reduced through shared memory, one
+//                                                     red.global.add.v4.f32 per CTA and 4 dims)
+// Thread mapping: the 32 lanes of a warp span the latent dims (VEC consecutive dims per lane and
+// 32*VEC-wide chunk), a warp owns RI rows, a CTA 8*RI rows; columns are streamed through a 3-stage
+// bulk-TMA pipeline together with the matching slice of the saved joint exponents s2_ij.
+// All FP32-pipe work is packed f32x2 (FFMA2/FMUL2/FADD2): ~8 issue slots per log-density.
+#include "tc_common.cuh"
+#include "tc_kernels.h"
+#include "tc_instr.h"
+
+namespace tcelbo {
+
+__device__ __forceinline__ float fset_le(float a, float b) {       // 1.0f if a <= b else 0.0f (FSET.BF)
+    float y; asm("set.le.f32.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b)); return y;
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int N> struct VecLd;
+template <> struct VecLd<1> { static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) { v[0] = *p; }
+                              static __device__ __forceinline__ void st(float* p, const float (&v)[1]) { *p = v[0]; } };
+template <> struct VecLd<2> { static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) {
+                                  const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+                              static __device__ __forceinline__ void st(float* p, const float (&v)[2]) {
+                                  *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); } };
+template <> struct VecLd<4> { static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+                                  const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+                              static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
+                                  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); } };
+
+template <int DPT> struct BwdGeom {
+    static constexpr int VEC = DPT < 4 ? DPT : 4;
+    static constexpr int NCH = DPT / VEC;
+    static constexpr int DP = 32 * DPT;
+    static constexpr int CH = 32 * VEC;
+    static constexpr int JT = (kTileFloats / DP) > 16 ? 16 : (kTileFloats / DP);      // columns per pipeline stage
+    static constexpr int JS = (1024 / DP) > 8 ? 8 : ((1024 / DP) < 1 ? 1 : (1024 / DP)); // columns per G staging buffer
+    static constexpr int GV = JS >= 2 ? 2 : 1;                                         // columns per gq vector load
+    static constexpr int NP = DPT >= 2 ? DPT / 2 : 1;                                  // f32x2 pairs per row
+};
+
+// One (row, column) pair of this lane's DPT dims, packed two dims per instruction.
+template <int DPT, bool kWeighted>
+__device__ __forceinline__ void bwd_pairs(const u64 (&mu2)[BwdGeom<DPT>::NP], const u64 (&zs2)[BwdGeom<DPT>::NP],
+                                          const u64 (&ns2)[BwdGeom<DPT>::NP], const float (&qmx)[2 * BwdGeom<DPT>::NP],
+                                          const u64 (&gps2)[BwdGeom<DPT>::NP], float gq, float rho,
+                                          u64 (&A2)[BwdGeom<DPT>::NP], u64 (&CR2)[BwdGeom<DPT>::NP], u64 (&G2)[BwdGeom<DPT>::NP]) {
+    constexpr int NP = BwdGeom<DPT>::NP;
+    const u64 gq2 = pack2(gq, gq);
+    const u64 rho2 = pack2(rho, rho);
+    const u64 k2 = pack2(kTwoLn2, kTwoLn2);
+    const u64 neg1 = pack2(-1.0f, -1.0f);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const u64 dl2 = ffma2(mu2[p], ns2[p], zs2[p]);
+        const u64 q2 = fmul2(dl2, dl2);
+        float q0, q1;
+        unpack2(q2, q0, q1);
+        const float c0 = fmin_nan(q0, qmx[2 * p]), c1 = fmin_nan(q1, qmx[2 * p + 1]);
+        u64 e2 = pack2(ex2(-c0), ex2(-c1));
+        if (kWeighted) e2 = fmul2(e2, rho2);
+        const u64 coef2 = ffma2(e2, gps2[p], gq2);
+        const u64 m2 = pack2(fset_le(q0, qmx[2 * p]), fset_le(q1, qmx[2 * p + 1]));
+        const u64 r2 = fmul2(coef2, m2);
+        const u64 t2 = fmul2(r2, dl2);
+        A2[p] = fadd2(A2[p], t2);
+        const u64 u2 = ffma2(pack2(c0, c1), k2, neg1);
+        CR2[p] = ffma2(r2, u2, CR2[p]);
+        G2[p] = ffma2(t2, ns2[p], G2[p]);
+    }
+}
+
+template <int DPT, int RI>
+__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+tc_bwd_fused_kernel(const BwdFusedArgs a) {
+    using GEO = BwdGeom<DPT>;
+    constexpr int VEC = GEO::VEC, NCH = GEO::NCH, DP = GEO::DP, CH = GEO::CH, JT = GEO::JT, JS = GEO::JS, GV = GEO::GV, NP = GEO::NP;
+    constexpr int TILE = JT * DP;
+    constexpr int ROWS = kBwdWarps * RI;
+    constexpr int GST = kBwdWarps * JS * DP;                                 // floats per G staging buffer
+    static_assert(DPT == 1 || DPT % 2 == 0, "dims per lane must pair up");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* mu_tiles = reinterpret_cast<float*>(smem_raw);                    // [kStages][TILE]
+    float* s2_tiles = mu_tiles + (size_t)kStages * TILE;                     // [kStages][ROWS][JT]
+    float* gq_buf = s2_tiles + (size_t)kStages * ROWS * JT;                  // [kBwdWarps][RI][JT]
+    float* gstage = gq_buf + (size_t)kBwdWarps * RI * JT;                    // [2][kBwdWarps][JS][DP]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gstage + 2 * (size_t)GST);
+    uint64_t* bar_empty = bar_full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * ROWS + warp * RI;
+
+    // ---- row constants and accumulators of this warp's RI rows (this lane's dims) -> registers
+    u64 zs2[RI][NP], ns2[RI][NP], gps2[RI][NP], A2[RI][NP], CR2[RI][NP];
+    float qmx[RI][2 * NP];
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+        const size_t base = (size_t)(row0 + r) * DP;
+        float vz[DPT], vn[DPT], vq[DPT], vg[DPT];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            float v[VEC];
+            VecLd<VEC>::ld(a.zs + base + c * CH + VEC * lane, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) vz[c * VEC + e] = v[e];
+            VecLd<VEC>::ld(a.ns + base + c * CH + VEC * lane, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) vn[c * VEC + e] = v[e];
+            VecLd<VEC>::ld(a.qmax + base + c * CH + VEC * lane, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) vq[c * VEC + e] = v[e];
+            VecLd<VEC>::ld(a.gps + base + c * CH + VEC * lane, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) vg[c * VEC + e] = v[e];
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int e0 = 2 * p, e1 = (DPT >= 2) ? 2 * p + 1 : 0;
+            zs2[r][p] = pack2(vz[e0], DPT >= 2 ? vz[e1] : 0.0f);
+            ns2[r][p] = pack2(vn[e0], DPT >= 2 ? vn[e1] : 0.0f);
+            gps2[r][p] = pack2(vg[e0], DPT >= 2 ? vg[e1] : 0.0f);
+            qmx[r][2 * p] = vq[e0];
+            qmx[r][2 * p + 1] = DPT >= 2 ? vq[e1] : 0.0f;
+            A2[r][p] = 0ull; CR2[r][p] = 0ull;
+        }
+    }
+
+    const int j0 = blockIdx.y * a.js_len;
+    const int j1 = min(a.bg_pad, j0 + a.js_len);
+    const int ntiles = (j1 - j0) / JT;
+    constexpr uint32_t kTxBytes = (TILE + ROWS * JT) * sizeof(float);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kBwdWarps); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {                                                // warp 0, all lanes
+        const int sn = t % kStages;
+        if (lane == 0) {
+            if (t >= kStages) mbar_wait(&bar_empty[sn], ((t / kStages) - 1) & 1);
+            mbar_arrive_expect_tx(&bar_full[sn], kTxBytes);
+            bulk_g2s(mu_tiles + (size_t)sn * TILE, a.mu_pad + (size_t)(j0 + t * JT) * DP, TILE * sizeof(float), &bar_full[sn]);
+        }
+        __syncwarp();
+        for (int r = lane; r < ROWS; r += 32)
+            bulk_g2s(s2_tiles + ((size_t)sn * ROWS + r) * JT,
+                     a.s2 + (size_t)(blockIdx.x * ROWS + r) * a.ld_s2 + (j0 + t * JT), JT * sizeof(float), &bar_full[sn]);
+    };
+    if (warp == 0 && ntiles > 0) issue(0);
+
+    float* gq = gq_buf + (size_t)warp * RI * JT;
+    int gbuf = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int st = t % kStages;
+        if (warp == 0 && t + 1 < ntiles) issue(t + 1);
+        mbar_wait(&bar_full[st], (t / kStages) & 1);
+        const float* tile = mu_tiles + (size_t)st * TILE;
+        const float* s2t = s2_tiles + ((size_t)st * ROWS + warp * RI) * JT;
+        const int jt0 = j0 + t * JT;
+        const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
+
+        // joint-term coefficients gJ_i * q_ij of this warp's rows for the tile
+        __syncwarp();
+        for (int idx = lane; idx < RI * JT; idx += 32) {
+            const int r = idx / JT, jj = idx % JT;
+            float rho = 1.0f, l2 = 0.0f;
+            if (special) weight_of(a.w, a.row_offset + row0 + r, jt0 + jj, rho, l2);
+            const float gjr = __ldg(a.gj + row0 + r), j2r = __ldg(a.J2 + row0 + r);
+            const float qv = ex2(l2 - s2t[idx] - j2r);
+            gq[idx] = (jt0 + jj < a.w.b_glob) ? gjr * qv : 0.0f;
+        }
+        __syncwarp();
+
+        for (int sub = 0; sub < JT; sub += JS) {
+            float* gst = gstage + (size_t)gbuf * GST + (size_t)warp * JS * DP;
+#pragma unroll 1
+            for (int g0 = 0; g0 < JS; g0 += GV) {
+                float gqv[RI][GV];
+#pragma unroll
+                for (int r = 0; r < RI; ++r) VecLd<GV>::ld(gq + r * JT + sub + g0, gqv[r]);
+#pragma unroll
+                for (int u = 0; u < GV; ++u) {
+                    const int jj = sub + g0 + u;
+                    u64 mu2[NP], G2[NP];
+                    {
+                        float vm[DPT];
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            float v[VEC];
+                            VecLd<VEC>::ld(tile + jj * DP + c * CH + VEC * lane, v);
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) vm[c * VEC + e] = v[e];
+                        }
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) { mu2[p] = pack2(vm[2 * p], DPT >= 2 ? vm[(2 * p + 1) % DPT] : 0.0f); G2[p] = 0ull; }
+                    }
+                    if (special) {
+#pragma unroll
+                        for (int r = 0; r < RI; ++r) {
+                            float rho, l2;
+                            weight_of(a.w, a.row_offset + row0 + r, jt0 + jj, rho, l2);
+                            bwd_pairs<DPT, true>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], rho, A2[r], CR2[r], G2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < RI; ++r)
+                            bwd_pairs<DPT, false>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], 1.0f, A2[r], CR2[r], G2);
+                    }
+                    // warp-partial column gradient -> staging buffer [warp][column][dim]
+                    float vg[DPT];
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        float lo, hi; unpack2(G2[p], lo, hi);
+                        vg[2 * p % DPT] = lo; if (DPT >= 2) vg[(2 * p + 1) % DPT] = hi;
+                    }
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        float v[VEC];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) v[e] = vg[c * VEC + e];
+                        VecLd<VEC>::st(gst + (g0 + u) * DP + c * CH + VEC * lane, v);
+                    }
+                }
+            }
+            __syncthreads();
+            // reduce the 8 warp partials of JS columns and add them to the global column accumulator
+            {
+                const float* gsb = gstage + (size_t)gbuf * GST;
+                for (int f = threadIdx.x; f < JS * DP / 4; f += kBwdWarps * 32) {
+                    const int col = f / (DP / 4), chunk = f % (DP / 4);
+                    float4 acc = *reinterpret_cast<const float4*>(gsb + col * DP + 4 * chunk);
+#pragma unroll
+                    for (int w = 1; w < kBwdWarps; ++w) {
+                        const float4 v = *reinterpret_cast<const float4*>(gsb + ((size_t)w * JS + col) * DP + 4 * chunk);
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    }
+                    red_add_v4(a.Gacc + (size_t)(jt0 + sub + col) * DP + 4 * chunk, acc.x, acc.y, acc.z, acc.w);
+                }
+            }
+            gbuf ^= 1;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[st]);
+    }
+
+    // ---- row-local partial sums of this (row block, column split)
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+        const size_t base = ((size_t)blockIdx.y * a.bl_pad + row0 + r) * DP;
+        float va[DPT], vc[DPT];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            float lo, hi;
+            unpack2(A2[r][p], lo, hi); va[2 * p % DPT] = lo; if (DPT >= 2) va[(2 * p + 1) % DPT] = hi;
+            unpack2(CR2[r][p], lo, hi); vc[2 * p % DPT] = lo; if (DPT >= 2) vc[(2 * p + 1) % DPT] = hi;
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            float v[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[e] = va[c * VEC + e];
+            VecLd<VEC>::st(a.Apart + base + c * CH + VEC * lane, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[e] = vc[c * VEC + e];
+            VecLd<VEC>::st(a.CRpart + base + c * CH + VEC * lane, v);
+        }
+    }
+}
+
+__global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
+    const int64_t n_row = (int64_t)a.b_loc * a.d;
+    const int64_t n_col = (int64_t)a.b_glob * a.d;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_row + n_col; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (idx < n_row) {
+            const int i = (int)(idx / a.d), dd = (int)(idx % a.d);
+            const size_t o = (size_t)i * a.dp + dd;
+            float sa = 0.0f, sc = 0.0f;
+            for (int s = 0; s < a.n_js; ++s) {
+                sa += a.Apart[(size_t)s * a.bl_pad * a.dp + o];
+                sc += a.CRpart[(size_t)s * a.bl_pad * a.dp + o];
+            }
+            a.grad_z[(int64_t)i * a.ldgz + dd] = kTwoLn2 * a.ns[o] * sa;
+            a.grad_lv[(int64_t)i * a.ldglv + dd] = a.vr[o] * sc;
+        } else {
+            const int64_t k = idx - n_row;
+            const int j = (int)(k / a.d), dd = (int)(k % a.d);
+            a.grad_mu[(int64_t)j * a.ldgmu + dd] = -kTwoLn2 * a.Gpart[(size_t)j * a.dp + dd];
+        }
+    }
+}
+
+template <int DPT, int RI>
+static cudaError_t launch_bwd_fused_t(const Plan& p, const BwdFusedArgs& a, cudaStream_t st) {
+    using GEO = BwdGeom<DPT>;
+    constexpr int ROWS = kBwdWarps * RI;
+    const size_t smem = ((size_t)kStages * GEO::JT * GEO::DP + (size_t)kStages * ROWS * GEO::JT + (size_t)kBwdWarps * RI * GEO::JT
+                         + 2 * (size_t)kBwdWarps * GEO::JS * GEO::DP) * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_bwd_fused_kernel<DPT, RI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    LaunchScope scope(kKernBwdRow, st);
+    tc_bwd_fused_kernel<DPT, RI><<<dim3(p.n_rb_bwr, p.n_js_bwr), kBwdWarps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, cudaStream_t st) {
+    switch (p.dpt) {
+        case 1:  return launch_bwd_fused_t<1, 4>(p, a, st);
+        case 2:  return launch_bwd_fused_t<2, 4>(p, a, st);
+        case 4:  return launch_bwd_fused_t<4, 4>(p, a, st);
+        case 8:  return launch_bwd_fused_t<8, 2>(p, a, st);
+        case 16: return launch_bwd_fused_t<16, 1>(p, a, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_bwd_fused_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st) {
+    const int64_t n = (int64_t)p.b_loc * p.d + (int64_t)p.b_glob * p.d;
+    int64_t g = (n + 255) / 256; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1;
+    LaunchScope scope(kKernNone, st);
+    bwd_fused_finalize_kernel<<<(int)g, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace tcelbo

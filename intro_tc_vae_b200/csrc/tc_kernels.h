@@ -44,6 +44,17 @@ struct BwdColArgs {
     Weights w;
 };
 
+struct BwdFusedArgs {
+    const float* zs; const float* ns; const float* qmax; const float* gps;   // [bl_pad][dp]
+    const float* gj; const float* J2;                                        // [bl_pad]
+    const float* mu_pad;                                                     // [bg_pad][dp]
+    const float* s2; int64_t ld_s2;
+    float* Apart; float* CRpart;                                             // [n_js][bl_pad][dp]
+    float* Gacc;                                                             // [bg_pad][dp], zeroed by the caller
+    int b_loc, bl_pad, bg_pad, row_offset, js_len;
+    Weights w;
+};
+
 struct BwdFinArgs {
     const float* Apart; const float* CRpart; const float* Gpart;
     const float* ns; const float* vr;
@@ -61,5 +72,7 @@ cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g
 cudaError_t launch_bwd_row(const Plan& p, const BwdRowArgs& a, cudaStream_t st);
 cudaError_t launch_bwd_col(const Plan& p, const BwdColArgs& a, cudaStream_t st);
 cudaError_t launch_bwd_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st);
+cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, cudaStream_t st);
+cudaError_t launch_bwd_fused_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st);
 
 }  // namespace tcelbo
