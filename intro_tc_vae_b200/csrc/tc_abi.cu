@@ -197,13 +197,13 @@ int tcelbo_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ld
         BwdFusedArgs ua;
         ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
         ua.s2 = s2; ua.ld_s2 = p.ld_s2; ua.Apart = Apart; ua.CRpart = CRpart; ua.Gacc = Gpart;
-        ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = p.js_len_bwr; ua.w = w;
+        ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = p.js_len_bwf; ua.w = w;
         if ((e = launch_bwd_fused(p, ua, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");
         BwdFinArgs fa;
         fa.Apart = Apart; fa.CRpart = CRpart; fa.Gpart = Gpart; fa.ns = ns; fa.vr = vr;
         fa.grad_z = grad_z; fa.ldgz = ldgz; fa.grad_lv = grad_logvar; fa.ldglv = ldglv; fa.grad_mu = grad_mu_all; fa.ldgmu = ldgmu;
         fa.b_loc = b_loc; fa.b_glob = b_glob; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.d = d; fa.dp = p.dp;
-        fa.n_js = p.n_js_bwr; fa.n_is = 1;
+        fa.n_js = p.n_js_bwf; fa.n_is = 1;
         if ((e = launch_bwd_fused_finalize(p, fa, st)) != cudaSuccess) return fail_cuda(e, "bwd_fused_finalize");
         return TCELBO_OK;
     }

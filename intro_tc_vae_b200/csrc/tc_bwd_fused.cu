@@ -42,7 +42,7 @@ template <int DPT> struct BwdGeom {
     static constexpr int CH = 32 * VEC;
     static constexpr int JT = (kTileFloats / DP) > 16 ? 16 : (kTileFloats / DP);      // columns per pipeline stage
     static constexpr int JS = (1024 / DP) > 8 ? 8 : ((1024 / DP) < 1 ? 1 : (1024 / DP)); // columns per G staging buffer
-    static constexpr int GV = JS >= 2 ? 2 : 1;                                         // columns per gq vector load
+    static constexpr int GV = JS >= 4 ? 4 : JS;                                        // columns per gq vector load
     static constexpr int NP = DPT >= 2 ? DPT / 2 : 1;                                  // f32x2 pairs per row
 };
 
@@ -77,33 +77,40 @@ __device__ __forceinline__ void bwd_pairs(const u64 (&mu2)[BwdGeom<DPT>::NP], co
     }
 }
 
+constexpr int kFusedWarps = 12;      // 384 threads x 168 registers = one CTA per SM, 3 warps per scheduler
+
 template <int DPT, int RI>
-__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+__global__ void __launch_bounds__(kFusedWarps * 32, 1)
 tc_bwd_fused_kernel(const BwdFusedArgs a) {
     using GEO = BwdGeom<DPT>;
     constexpr int VEC = GEO::VEC, NCH = GEO::NCH, DP = GEO::DP, CH = GEO::CH, JT = GEO::JT, JS = GEO::JS, GV = GEO::GV, NP = GEO::NP;
+    constexpr int NW = kFusedWarps;
     constexpr int TILE = JT * DP;
-    constexpr int ROWS = kBwdWarps * RI;
-    constexpr int GST = kBwdWarps * JS * DP;                                 // floats per G staging buffer
+    constexpr int ROWS = NW * RI;
+    constexpr int GST = NW * JS * DP;                                        // floats per G staging buffer
     static_assert(DPT == 1 || DPT % 2 == 0, "dims per lane must pair up");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* mu_tiles = reinterpret_cast<float*>(smem_raw);                    // [kStages][TILE]
     float* s2_tiles = mu_tiles + (size_t)kStages * TILE;                     // [kStages][ROWS][JT]
-    float* gq_buf = s2_tiles + (size_t)kStages * ROWS * JT;                  // [kBwdWarps][RI][JT]
-    float* gstage = gq_buf + (size_t)kBwdWarps * RI * JT;                    // [2][kBwdWarps][JS][DP]
+    float* gq_buf = s2_tiles + (size_t)kStages * ROWS * JT;                  // [NW][RI][JT]
+    float* gstage = gq_buf + (size_t)NW * RI * JT;                           // [2][NW][JS][DP]
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(gstage + 2 * (size_t)GST);
     uint64_t* bar_empty = bar_full + kStages;
+    uint64_t* g_full = bar_empty + kStages;                                  // [2] staging buffer written by all warps
+    uint64_t* g_empty = g_full + 2;                                          // [2] staging buffer reduced by all warps
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * ROWS + warp * RI;
 
-    // ---- row constants and accumulators of this warp's RI rows (this lane's dims) -> registers
+    // ---- row constants and accumulators of this warp's RI rows (this lane's dims) -> registers.
+    //      Rows past the padded batch are clamped for loads and carry zero coefficients.
     u64 zs2[RI][NP], ns2[RI][NP], gps2[RI][NP], A2[RI][NP], CR2[RI][NP];
     float qmx[RI][2 * NP];
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
-        const size_t base = (size_t)(row0 + r) * DP;
+        const bool valid = (row0 + r) < a.bl_pad;
+        const size_t base = (size_t)min(row0 + r, a.bl_pad - 1) * DP;
         float vz[DPT], vn[DPT], vq[DPT], vg[DPT];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -119,7 +126,7 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
             for (int e = 0; e < VEC; ++e) vq[c * VEC + e] = v[e];
             VecLd<VEC>::ld(a.gps + base + c * CH + VEC * lane, v);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) vg[c * VEC + e] = v[e];
+            for (int e = 0; e < VEC; ++e) vg[c * VEC + e] = valid ? v[e] : 0.0f;
         }
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
@@ -139,7 +146,8 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
     constexpr uint32_t kTxBytes = (TILE + ROWS * JT) * sizeof(float);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kBwdWarps); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NW); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&g_full[s], NW); mbar_init(&g_empty[s], NW); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -154,12 +162,31 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
         __syncwarp();
         for (int r = lane; r < ROWS; r += 32)
             bulk_g2s(s2_tiles + ((size_t)sn * ROWS + r) * JT,
-                     a.s2 + (size_t)(blockIdx.x * ROWS + r) * a.ld_s2 + (j0 + t * JT), JT * sizeof(float), &bar_full[sn]);
+                     a.s2 + (size_t)min((int)(blockIdx.x * ROWS + r), a.bl_pad - 1) * a.ld_s2 + (j0 + t * JT), JT * sizeof(float), &bar_full[sn]);
     };
     if (warp == 0 && ntiles > 0) issue(0);
 
+    // reduce this thread's share of staging buffer (k & 1) (sub-tile k, columns starting at col0) into Gacc
+    auto reduce_share = [&](int k, int col0) {
+        const int b = k & 1;
+        mbar_wait(&g_full[b], (k >> 1) & 1);
+        const float* gsb = gstage + (size_t)b * GST;
+        for (int f = threadIdx.x; f < JS * DP / 4; f += NW * 32) {
+            const int col = f / (DP / 4), chunk = f % (DP / 4);
+            float4 acc = *reinterpret_cast<const float4*>(gsb + col * DP + 4 * chunk);
+#pragma unroll
+            for (int w = 1; w < NW; ++w) {
+                const float4 v = *reinterpret_cast<const float4*>(gsb + ((size_t)w * JS + col) * DP + 4 * chunk);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            red_add_v4(a.Gacc + (size_t)(col0 + col) * DP + 4 * chunk, acc.x, acc.y, acc.z, acc.w);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&g_empty[b]);
+    };
+
     float* gq = gq_buf + (size_t)warp * RI * JT;
-    int gbuf = 0;
+    int k = 0, prev_col0 = 0;                                                // running sub-tile index
     for (int t = 0; t < ntiles; ++t) {
         const int st = t % kStages;
         if (warp == 0 && t + 1 < ntiles) issue(t + 1);
@@ -173,16 +200,20 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
         __syncwarp();
         for (int idx = lane; idx < RI * JT; idx += 32) {
             const int r = idx / JT, jj = idx % JT;
+            const int row = row0 + r;
             float rho = 1.0f, l2 = 0.0f;
-            if (special) weight_of(a.w, a.row_offset + row0 + r, jt0 + jj, rho, l2);
-            const float gjr = __ldg(a.gj + row0 + r), j2r = __ldg(a.J2 + row0 + r);
+            if (special) weight_of(a.w, a.row_offset + row, jt0 + jj, rho, l2);
+            const int rowc = min(row, a.bl_pad - 1);
+            const float gjr = __ldg(a.gj + rowc), j2r = __ldg(a.J2 + rowc);
             const float qv = ex2(l2 - s2t[idx] - j2r);
-            gq[idx] = (jt0 + jj < a.w.b_glob) ? gjr * qv : 0.0f;
+            gq[idx] = (jt0 + jj < a.w.b_glob && row < a.b_loc) ? gjr * qv : 0.0f;
         }
         __syncwarp();
 
-        for (int sub = 0; sub < JT; sub += JS) {
-            float* gst = gstage + (size_t)gbuf * GST + (size_t)warp * JS * DP;
+        for (int sub = 0; sub < JT; sub += JS, ++k) {
+            const int b = k & 1;
+            if (k >= 2) mbar_wait(&g_empty[b], ((k >> 1) - 1) & 1);           // everyone finished reducing sub-tile k-2
+            float* gst = gstage + (size_t)b * GST + (size_t)warp * JS * DP;
 #pragma unroll 1
             for (int g0 = 0; g0 < JS; g0 += GV) {
                 float gqv[RI][GV];
@@ -232,30 +263,20 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
                     }
                 }
             }
-            __syncthreads();
-            // reduce the 8 warp partials of JS columns and add them to the global column accumulator
-            {
-                const float* gsb = gstage + (size_t)gbuf * GST;
-                for (int f = threadIdx.x; f < JS * DP / 4; f += kBwdWarps * 32) {
-                    const int col = f / (DP / 4), chunk = f % (DP / 4);
-                    float4 acc = *reinterpret_cast<const float4*>(gsb + col * DP + 4 * chunk);
-#pragma unroll
-                    for (int w = 1; w < kBwdWarps; ++w) {
-                        const float4 v = *reinterpret_cast<const float4*>(gsb + ((size_t)w * JS + col) * DP + 4 * chunk);
-                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                    }
-                    red_add_v4(a.Gacc + (size_t)(jt0 + sub + col) * DP + 4 * chunk, acc.x, acc.y, acc.z, acc.w);
-                }
-            }
-            gbuf ^= 1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&g_full[b]);
+            if (k >= 1) reduce_share(k - 1, prev_col0);                      // the other buffer: its writers are long done
+            prev_col0 = jt0 + sub;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[st]);
     }
+    if (k >= 1) reduce_share(k - 1, prev_col0);
 
     // ---- row-local partial sums of this (row block, column split)
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
+        if (row0 + r >= a.bl_pad) continue;
         const size_t base = ((size_t)blockIdx.y * a.bl_pad + row0 + r) * DP;
         float va[DPT], vc[DPT];
 #pragma unroll
@@ -302,9 +323,10 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
 template <int DPT, int RI>
 static cudaError_t launch_bwd_fused_t(const Plan& p, const BwdFusedArgs& a, cudaStream_t st) {
     using GEO = BwdGeom<DPT>;
-    constexpr int ROWS = kBwdWarps * RI;
-    const size_t smem = ((size_t)kStages * GEO::JT * GEO::DP + (size_t)kStages * ROWS * GEO::JT + (size_t)kBwdWarps * RI * GEO::JT
-                         + 2 * (size_t)kBwdWarps * GEO::JS * GEO::DP) * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+    constexpr int ROWS = kFusedWarps * RI;
+    const size_t smem = ((size_t)kStages * GEO::JT * GEO::DP + (size_t)kStages * ROWS * GEO::JT + (size_t)kFusedWarps * RI * GEO::JT
+                         + 2 * (size_t)kFusedWarps * GEO::JS * GEO::DP) * sizeof(float) + (2 * kStages + 4) * sizeof(uint64_t);
+    const int n_rb = (p.bl_pad + ROWS - 1) / ROWS;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_bwd_fused_kernel<DPT, RI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -312,7 +334,7 @@ static cudaError_t launch_bwd_fused_t(const Plan& p, const BwdFusedArgs& a, cuda
         configured = true;
     }
     LaunchScope scope(kKernBwdRow, st);
-    tc_bwd_fused_kernel<DPT, RI><<<dim3(p.n_rb_bwr, p.n_js_bwr), kBwdWarps * 32, smem, st>>>(a);
+    tc_bwd_fused_kernel<DPT, RI><<<dim3(n_rb, p.n_js_bwf), kFusedWarps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,7 @@ struct Plan {
     // forward / backward-row pass: grid (n_rb, n_js)
     int fwd_rows, n_rb_fwd, n_js_fwd, js_len_fwd;
     int bwr_rows, bwr_ri, n_rb_bwr, n_js_bwr, js_len_bwr;
+    int bwf_rows, n_js_bwf, js_len_bwf;   // fused backward sweep: 12 warps x bwr_ri rows per CTA, one CTA per SM
     // backward-column pass: grid (n_cb, n_is)
     int bwc_cols, bwc_rj, bwc_it, n_cb, n_is, is_len;
     // workspace (byte offsets)
@@ -75,6 +76,18 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
         p.js_len_bwr = (int)round_up((p.bg_pad + want - 1) / want, p.jt);
         p.n_js_bwr = (p.bg_pad + p.js_len_bwr - 1) / p.js_len_bwr;
     }
+    // ---- fused backward sweep
+    p.bwf_rows = 12 * p.bwr_ri;
+    {
+        const int n_rb = (p.bl_pad + p.bwf_rows - 1) / p.bwf_rows;
+        const int slots = sms;                                 // one resident CTA per SM
+        const int min_len = p.jt * 4;
+        int max_js = p.bg_pad / min_len; if (max_js < 1) max_js = 1;
+        int want = (slots * 8 + n_rb - 1) / n_rb;
+        if (want < 1) want = 1; if (want > max_js) want = max_js;
+        p.js_len_bwf = (int)round_up((p.bg_pad + want - 1) / want, p.jt);
+        p.n_js_bwf = (p.bg_pad + p.js_len_bwf - 1) / p.js_len_bwf;
+    }
     // ---- backward column pass (grad_mu): a CTA owns bwc_cols columns and a range of is_len rows
     p.bwc_rj = p.dpt >= 16 ? 2 : (p.dpt >= 8 ? 4 : 8);
     p.bwc_cols = kBwdWarps * p.bwc_rj;
@@ -111,8 +124,9 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     size_t b = 0;
     p.boff_gps = b; b = align256(b + row_arr);
     p.boff_gj = b;  b = align256(b + (size_t)p.bl_pad * sizeof(float));
-    p.boff_A = b;   b = align256(b + (size_t)p.n_js_bwr * row_arr);
-    p.boff_CR = b;  b = align256(b + (size_t)p.n_js_bwr * row_arr);
+    const int n_js_max = p.n_js_bwr > p.n_js_bwf ? p.n_js_bwr : p.n_js_bwf;
+    p.boff_A = b;   b = align256(b + (size_t)n_js_max * row_arr);
+    p.boff_CR = b;  b = align256(b + (size_t)n_js_max * row_arr);
     p.boff_G = b;   b = align256(b + (size_t)p.n_is * col_arr);
     p.bwd_bytes = b;
     return true;
