@@ -141,6 +141,8 @@ long long tcelbo_launch_count(void);
  * 3 = backward column sweep, 0 = off) with cudaEventRecord(start) / cudaEventRecord(stop) on its stream;
  * the events are cudaEvent_t handles owned by the caller. */
 int tcelbo_profile_events(int kernel_id, void* start_event, void* stop_event);
+/* Kernel-variant selection for tuning runs ("bwd_variant": -1 = built-in choice). */
+int tcelbo_set_tuning(const char* key, int value);
 /* MUFU.EX2 saturation probe: `ctas` blocks of 256 threads, 8*iters dependent-chain ex2 per thread. */
 int tcelbo_ex2_peak(float* scratch, int iters, int ctas, void* stream);
 

@@ -197,13 +197,14 @@ int tcelbo_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ld
         BwdFusedArgs ua;
         ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
         ua.s2 = s2; ua.ld_s2 = p.ld_s2; ua.Apart = Apart; ua.CRpart = CRpart; ua.Gacc = Gpart;
-        ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = p.js_len_bwf; ua.w = w;
-        if ((e = launch_bwd_fused(p, ua, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");
+        ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = 0; ua.w = w;
+        int n_js_fused = 1;
+        if ((e = launch_bwd_fused(p, ua, &n_js_fused, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");
         BwdFinArgs fa;
         fa.Apart = Apart; fa.CRpart = CRpart; fa.Gpart = Gpart; fa.ns = ns; fa.vr = vr;
         fa.grad_z = grad_z; fa.ldgz = ldgz; fa.grad_lv = grad_logvar; fa.ldglv = ldglv; fa.grad_mu = grad_mu_all; fa.ldgmu = ldgmu;
         fa.b_loc = b_loc; fa.b_glob = b_glob; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.d = d; fa.dp = p.dp;
-        fa.n_js = p.n_js_bwf; fa.n_is = 1;
+        fa.n_js = n_js_fused; fa.n_is = 1;
         if ((e = launch_bwd_fused_finalize(p, fa, st)) != cudaSuccess) return fail_cuda(e, "bwd_fused_finalize");
         return TCELBO_OK;
     }
@@ -290,6 +291,11 @@ int tcelbo_profile_events(int kernel_id, void* start_event, void* stop_event) {
     in.ev_start = static_cast<cudaEvent_t>(start_event);
     in.ev_stop = static_cast<cudaEvent_t>(stop_event);
     return TCELBO_OK;
+}
+
+int tcelbo_set_tuning(const char* key, int value) {
+    if (key && std::strcmp(key, "bwd_variant") == 0) { set_bwd_variant(value); return TCELBO_OK; }
+    return fail(TCELBO_ERR_INVALID, "unknown tuning key");
 }
 
 int tcelbo_ex2_peak(float* scratch, int iters, int ctas, void* stream) {

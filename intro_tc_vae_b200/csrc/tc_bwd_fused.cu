@@ -4,12 +4,14 @@
 //     A_id   = sum_j r dl          -> grad_z        (row-local, registers)
 //     CR_id  = sum_j r (2 ln2 qc - 1) -> grad_logvar (row-local, registers)
 //     G_jd   = sum_i r dl ns_id    -> grad_mu       (column sum over rows: warp-partial in registers,
-//                                                     8 warps reduced through shared memory, one
+//                                                     NW warps reduced through shared memory, one
 //                                                     red.global.add.v4.f32 per CTA and 4 dims)
 // Thread mapping: the 32 lanes of a warp span the latent dims (VEC consecutive dims per lane and
-// 32*VEC-wide chunk), a warp owns RI rows, a CTA 8*RI rows; columns are streamed through a 3-stage
-// bulk-TMA pipeline together with the matching slice of the saved joint exponents s2_ij.
-// All FP32-pipe work is packed f32x2 (FFMA2/FMUL2/FADD2): ~8 issue slots per log-density.
+// 32*VEC-wide chunk), a warp owns RI rows, a CTA NW*RI rows; columns are streamed through a 3-stage
+// bulk-TMA pipeline together with the matching slice of the saved joint exponents s2_ij.  The column
+// gradient is handed from the warps to the reduction through two staging buffers guarded by mbarriers,
+// so warps never wait for each other at a block-wide barrier.
+// All FP32-pipe work is packed f32x2 (FFMA2/FMUL2/FADD2): ~7.5 issue slots per log-density.
 #include "tc_common.cuh"
 #include "tc_kernels.h"
 #include "tc_instr.h"
@@ -35,24 +37,22 @@ template <> struct VecLd<4> { static __device__ __forceinline__ void ld(const fl
                               static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
                                   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); } };
 
-template <int DPT> struct BwdGeom {
+template <int DPT, int JS_> struct BwdGeom {
     static constexpr int VEC = DPT < 4 ? DPT : 4;
     static constexpr int NCH = DPT / VEC;
     static constexpr int DP = 32 * DPT;
     static constexpr int CH = 32 * VEC;
     static constexpr int JT = (kTileFloats / DP) > 16 ? 16 : (kTileFloats / DP);      // columns per pipeline stage
-    static constexpr int JS = (1024 / DP) > 8 ? 8 : ((1024 / DP) < 1 ? 1 : (1024 / DP)); // columns per G staging buffer
+    static constexpr int JS = JS_ > JT ? JT : JS_;                                     // columns per G staging buffer
     static constexpr int GV = JS >= 4 ? 4 : JS;                                        // columns per gq vector load
     static constexpr int NP = DPT >= 2 ? DPT / 2 : 1;                                  // f32x2 pairs per row
 };
 
 // One (row, column) pair of this lane's DPT dims, packed two dims per instruction.
-template <int DPT, bool kWeighted>
-__device__ __forceinline__ void bwd_pairs(const u64 (&mu2)[BwdGeom<DPT>::NP], const u64 (&zs2)[BwdGeom<DPT>::NP],
-                                          const u64 (&ns2)[BwdGeom<DPT>::NP], const float (&qmx)[2 * BwdGeom<DPT>::NP],
-                                          const u64 (&gps2)[BwdGeom<DPT>::NP], float gq, float rho,
-                                          u64 (&A2)[BwdGeom<DPT>::NP], u64 (&CR2)[BwdGeom<DPT>::NP], u64 (&G2)[BwdGeom<DPT>::NP]) {
-    constexpr int NP = BwdGeom<DPT>::NP;
+template <int NP, bool kWeighted>
+__device__ __forceinline__ void bwd_pairs(const u64 (&mu2)[NP], const u64 (&zs2)[NP], const u64 (&ns2)[NP],
+                                          const float (&qmx)[2 * NP], const u64 (&gps2)[NP], float gq, float rho,
+                                          u64 (&A2)[NP], u64 (&CR2)[NP], u64 (&G2)[NP]) {
     const u64 gq2 = pack2(gq, gq);
     const u64 rho2 = pack2(rho, rho);
     const u64 k2 = pack2(kTwoLn2, kTwoLn2);
@@ -77,17 +77,57 @@ __device__ __forceinline__ void bwd_pairs(const u64 (&mu2)[BwdGeom<DPT>::NP], co
     }
 }
 
-constexpr int kFusedWarps = 12;      // 384 threads x 168 registers = one CTA per SM, 3 warps per scheduler
+// Same arithmetic for a group of RG rows in two phases: every MUFU of the group is issued before any
+// of its results is consumed, so the ex2 latency overlaps the other rows' FP32 work inside one warp.
+template <int NP, int RG, bool kWeighted>
+__device__ __forceinline__ void bwd_rows_phased(const u64 (&mu2)[NP], const u64 (*zs2)[NP], const u64 (*ns2)[NP],
+                                                const float (*qmx)[2 * NP], const u64 (*gps2)[NP],
+                                                const float* gq, int gq_stride, const float* rho,
+                                                u64 (*A2)[NP], u64 (*CR2)[NP], u64 (&G2)[NP]) {
+    const u64 k2 = pack2(kTwoLn2, kTwoLn2);
+    const u64 neg1 = pack2(-1.0f, -1.0f);
+    u64 dl2[RG][NP], e2[RG][NP], m2[RG][NP], u2[RG][NP];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            dl2[r][p] = ffma2(mu2[p], ns2[r][p], zs2[r][p]);
+            const u64 q2 = fmul2(dl2[r][p], dl2[r][p]);
+            float q0, q1;
+            unpack2(q2, q0, q1);
+            const float c0 = fmin_nan(q0, qmx[r][2 * p]), c1 = fmin_nan(q1, qmx[r][2 * p + 1]);
+            e2[r][p] = pack2(ex2(-c0), ex2(-c1));
+            m2[r][p] = pack2(fset_le(q0, qmx[r][2 * p]), fset_le(q1, qmx[r][2 * p + 1]));
+            u2[r][p] = ffma2(pack2(c0, c1), k2, neg1);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+        const float g = gq[r * gq_stride];
+        const u64 gq2 = pack2(g, g);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            u64 e = e2[r][p];
+            if (kWeighted) e = fmul2(e, pack2(rho[r], rho[r]));
+            const u64 coef2 = ffma2(e, gps2[r][p], gq2);
+            const u64 r2 = fmul2(coef2, m2[r][p]);
+            const u64 t2 = fmul2(r2, dl2[r][p]);
+            A2[r][p] = fadd2(A2[r][p], t2);
+            CR2[r][p] = ffma2(r2, u2[r][p], CR2[r][p]);
+            G2[p] = ffma2(t2, ns2[r][p], G2[p]);
+        }
+    }
+}
 
-template <int DPT, int RI>
-__global__ void __launch_bounds__(kFusedWarps * 32, 1)
+template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED>
+__global__ void __launch_bounds__(NW * 32, MINB)
 tc_bwd_fused_kernel(const BwdFusedArgs a) {
-    using GEO = BwdGeom<DPT>;
+    using GEO = BwdGeom<DPT, JS_>;
     constexpr int VEC = GEO::VEC, NCH = GEO::NCH, DP = GEO::DP, CH = GEO::CH, JT = GEO::JT, JS = GEO::JS, GV = GEO::GV, NP = GEO::NP;
-    constexpr int NW = kFusedWarps;
     constexpr int TILE = JT * DP;
     constexpr int ROWS = NW * RI;
     constexpr int GST = NW * JS * DP;                                        // floats per G staging buffer
+    constexpr int RG = (RI % 2 == 0) ? 2 : 1;                                // rows per phase group
     static_assert(DPT == 1 || DPT % 2 == 0, "dims per lane must pair up");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -236,16 +276,30 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
                         for (int p = 0; p < NP; ++p) { mu2[p] = pack2(vm[2 * p], DPT >= 2 ? vm[(2 * p + 1) % DPT] : 0.0f); G2[p] = 0ull; }
                     }
                     if (special) {
+                        float rho[RI];
 #pragma unroll
-                        for (int r = 0; r < RI; ++r) {
-                            float rho, l2;
-                            weight_of(a.w, a.row_offset + row0 + r, jt0 + jj, rho, l2);
-                            bwd_pairs<DPT, true>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], rho, A2[r], CR2[r], G2);
+                        for (int r = 0; r < RI; ++r) { float l2; weight_of(a.w, a.row_offset + row0 + r, jt0 + jj, rho[r], l2); }
+                        if (PHASED) {
+#pragma unroll
+                            for (int rg = 0; rg < RI; rg += RG)
+                                bwd_rows_phased<NP, RG, true>(mu2, &zs2[rg], &ns2[rg], &qmx[rg], &gps2[rg], &gqv[rg][u], GV, &rho[rg],
+                                                              &A2[rg], &CR2[rg], G2);
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < RI; ++r)
+                                bwd_pairs<NP, true>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], rho[r], A2[r], CR2[r], G2);
                         }
                     } else {
+                        if (PHASED) {
 #pragma unroll
-                        for (int r = 0; r < RI; ++r)
-                            bwd_pairs<DPT, false>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], 1.0f, A2[r], CR2[r], G2);
+                            for (int rg = 0; rg < RI; rg += RG)
+                                bwd_rows_phased<NP, RG, false>(mu2, &zs2[rg], &ns2[rg], &qmx[rg], &gps2[rg], &gqv[rg][u], GV, nullptr,
+                                                               &A2[rg], &CR2[rg], G2);
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < RI; ++r)
+                                bwd_pairs<NP, false>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], 1.0f, A2[r], CR2[r], G2);
+                        }
                     }
                     // warp-partial column gradient -> staging buffer [warp][column][dim]
                     float vg[DPT];
@@ -320,31 +374,58 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
     }
 }
 
-template <int DPT, int RI>
-static cudaError_t launch_bwd_fused_t(const Plan& p, const BwdFusedArgs& a, cudaStream_t st) {
-    using GEO = BwdGeom<DPT>;
-    constexpr int ROWS = kFusedWarps * RI;
-    const size_t smem = ((size_t)kStages * GEO::JT * GEO::DP + (size_t)kStages * ROWS * GEO::JT + (size_t)kFusedWarps * RI * GEO::JT
-                         + 2 * (size_t)kFusedWarps * GEO::JS * GEO::DP) * sizeof(float) + (2 * kStages + 4) * sizeof(uint64_t);
-    const int n_rb = (p.bl_pad + ROWS - 1) / ROWS;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_bwd_fused_kernel<DPT, RI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// ------------------------------------------------------------------------------------------------------
+// launch: the column split is planned here because it depends on the variant's CTA shape
+// ------------------------------------------------------------------------------------------------------
+static int g_bwd_variant = -1;      // -1: default per shape; set through tcelbo_set_tuning("bwd_variant", v)
+void set_bwd_variant(int v) { g_bwd_variant = v; }
+
+template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED>
+static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, int* n_js_out, cudaStream_t st) {
+    using GEO = BwdGeom<DPT, JS_>;
+    constexpr int ROWS = NW * RI;
+    const size_t smem = ((size_t)kStages * GEO::JT * GEO::DP + (size_t)kStages * ROWS * GEO::JT + (size_t)NW * RI * GEO::JT
+                         + 2 * (size_t)NW * GEO::JS * GEO::DP) * sizeof(float) + (2 * kStages + 4) * sizeof(uint64_t);
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        auto kern = tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, smem);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = occ > 0 ? occ : 1;
     }
+    const int n_rb = (p.bl_pad + ROWS - 1) / ROWS;
+    int n_js, js_len;
+    choose_splits(n_rb, p.sms * ctas_per_sm, p.bg_pad, p.jt, 4, n_js, js_len);
+    a.js_len = js_len;
+    *n_js_out = n_js;
     LaunchScope scope(kKernBwdRow, st);
-    tc_bwd_fused_kernel<DPT, RI><<<dim3(n_rb, p.n_js_bwf), kFusedWarps * 32, smem, st>>>(a);
+    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED><<<dim3(n_rb, n_js), NW * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, cudaStream_t st) {
+cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out, cudaStream_t st) {
     switch (p.dpt) {
-        case 1:  return launch_bwd_fused_t<1, 4>(p, a, st);
-        case 2:  return launch_bwd_fused_t<2, 4>(p, a, st);
-        case 4:  return launch_bwd_fused_t<4, 4>(p, a, st);
-        case 8:  return launch_bwd_fused_t<8, 2>(p, a, st);
-        case 16: return launch_bwd_fused_t<16, 1>(p, a, st);
+        case 1:  return launch_bwd_fused_t<1, 4, 12, 1, 8, false>(p, a, n_js_out, st);
+        case 2:  return launch_bwd_fused_t<2, 4, 12, 1, 8, false>(p, a, n_js_out, st);
+        case 4:
+            switch (g_bwd_variant) {                 // tuning matrix for the headline shape (D = 128)
+                case 1:  return launch_bwd_fused_t<4, 4, 12, 1, 8, true >(p, a, n_js_out, st);
+                case 2:  return launch_bwd_fused_t<4, 4, 8, 2, 8, false>(p, a, n_js_out, st);
+                case 3:  return launch_bwd_fused_t<4, 4, 8, 2, 8, true >(p, a, n_js_out, st);
+                case 4:  return launch_bwd_fused_t<4, 2, 8, 3, 4, false>(p, a, n_js_out, st);
+                case 5:  return launch_bwd_fused_t<4, 2, 8, 3, 4, true >(p, a, n_js_out, st);
+                case 6:  return launch_bwd_fused_t<4, 2, 16, 1, 8, true >(p, a, n_js_out, st);
+                case 7:  return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);
+                case 8:  return launch_bwd_fused_t<4, 2, 12, 2, 4, true >(p, a, n_js_out, st);
+                case 9:  return launch_bwd_fused_t<4, 4, 16, 1, 8, true >(p, a, n_js_out, st);
+                case 10: return launch_bwd_fused_t<4, 2, 16, 2, 4, true >(p, a, n_js_out, st);
+                default: return launch_bwd_fused_t<4, 4, 12, 1, 8, false>(p, a, n_js_out, st);
+            }
+        case 8:  return launch_bwd_fused_t<8, 2, 12, 1, 4, false>(p, a, n_js_out, st);
+        case 16: return launch_bwd_fused_t<16, 1, 12, 1, 2, false>(p, a, n_js_out, st);
         default: return cudaErrorInvalidValue;
     }
 }

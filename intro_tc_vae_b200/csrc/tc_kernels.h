@@ -72,7 +72,8 @@ cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g
 cudaError_t launch_bwd_row(const Plan& p, const BwdRowArgs& a, cudaStream_t st);
 cudaError_t launch_bwd_col(const Plan& p, const BwdColArgs& a, cudaStream_t st);
 cudaError_t launch_bwd_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st);
-cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, cudaStream_t st);
+cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out, cudaStream_t st);
+void set_bwd_variant(int v);
 cudaError_t launch_bwd_fused_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st);
 
 }  // namespace tcelbo

@@ -16,6 +16,7 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 struct Plan {
     // padded problem
+    int sms;
     int d, dp, dpt;            // dp = power of two >= max(d, 32); dpt = dp / 32 (floats per lane / lanes per row)
     int b_loc, b_glob, bl_pad, bg_pad;
     int jt;                    // column-tile height (rows of mu per stage) = kTileFloats / dp
@@ -38,6 +39,28 @@ struct Plan {
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
+constexpr int kMaxSplits = 16;        // upper bound on column/row splits (bounds the partial-sum scratch)
+
+// Pick how many ranges to cut `len` (a multiple of `quantum`) into so that n_blocks * n_splits CTAs fill
+// `slots` resident CTA slots in whole waves: minimises ceil(ctas / slots) / n_splits, i.e. the time of
+// the sweep in units of one full-length CTA.  Ties go to fewer splits (less partial-sum traffic).
+inline void choose_splits(int n_blocks, int slots, int len, int quantum, int min_quanta, int& n_splits, int& split_len) {
+    int max_splits = len / (quantum * min_quanta);
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > kMaxSplits) max_splits = kMaxSplits;
+    double best = 1e30; int best_n = 1;
+    for (int n = 1; n <= max_splits; ++n) {
+        const int sl = (int)round_up((len + n - 1) / n, quantum);
+        const int n_eff = (len + sl - 1) / sl;
+        const long long ctas = (long long)n_blocks * n_eff;
+        const double waves = (double)((ctas + slots - 1) / slots);
+        const double cost = waves * (double)sl;               // time ~ waves x columns per CTA
+        if (cost < best * 0.999) { best = cost; best_n = n_eff; }
+    }
+    split_len = (int)round_up((len + best_n - 1) / best_n, quantum);
+    n_splits = (len + split_len - 1) / split_len;
+}
+
 // `sms` = multiprocessor count of the current device (148 on B200).
 inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int sms) {
     if (b_loc < 1 || b_glob < 1 || d < 1 || d > 512) return false;
@@ -54,54 +77,22 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     // ---- forward: a CTA owns fwd_rows rows and a contiguous range of js_len columns
     p.fwd_rows = kFwdWarps * (32 / p.dpt);
     p.n_rb_fwd = p.bl_pad / p.fwd_rows;
-    {
-        const int slots = sms * 3;                             // resident CTAs at 3 per SM
-        const int min_len = p.jt * 4;
-        int max_js = p.bg_pad / min_len; if (max_js < 1) max_js = 1;
-        int want = (slots * 8 + p.n_rb_fwd - 1) / p.n_rb_fwd;
-        if (want < 1) want = 1; if (want > max_js) want = max_js;
-        p.js_len_fwd = (int)round_up((p.bg_pad + want - 1) / want, p.jt);
-        p.n_js_fwd = (p.bg_pad + p.js_len_fwd - 1) / p.js_len_fwd;
-    }
+    choose_splits(p.n_rb_fwd, sms * 3, p.bg_pad, p.jt, 4, p.n_js_fwd, p.js_len_fwd);   // 3 resident CTAs per SM
     // ---- backward row pass (row-local gradients)
     p.bwr_ri = p.dpt >= 16 ? 1 : (p.dpt >= 8 ? 2 : 4);
     p.bwr_rows = kBwdWarps * p.bwr_ri;
     p.n_rb_bwr = p.bl_pad / p.bwr_rows;
-    {
-        const int slots = sms * 2;
-        const int min_len = p.jt * 4;
-        int max_js = p.bg_pad / min_len; if (max_js < 1) max_js = 1;
-        int want = (slots * 8 + p.n_rb_bwr - 1) / p.n_rb_bwr;
-        if (want < 1) want = 1; if (want > max_js) want = max_js;
-        p.js_len_bwr = (int)round_up((p.bg_pad + want - 1) / want, p.jt);
-        p.n_js_bwr = (p.bg_pad + p.js_len_bwr - 1) / p.js_len_bwr;
-    }
+    choose_splits(p.n_rb_bwr, sms * 2, p.bg_pad, p.jt, 4, p.n_js_bwr, p.js_len_bwr);
     // ---- fused backward sweep
-    p.bwf_rows = 12 * p.bwr_ri;
-    {
-        const int n_rb = (p.bl_pad + p.bwf_rows - 1) / p.bwf_rows;
-        const int slots = sms;                                 // one resident CTA per SM
-        const int min_len = p.jt * 4;
-        int max_js = p.bg_pad / min_len; if (max_js < 1) max_js = 1;
-        int want = (slots * 8 + n_rb - 1) / n_rb;
-        if (want < 1) want = 1; if (want > max_js) want = max_js;
-        p.js_len_bwf = (int)round_up((p.bg_pad + want - 1) / want, p.jt);
-        p.n_js_bwf = (p.bg_pad + p.js_len_bwf - 1) / p.js_len_bwf;
-    }
+    p.bwf_rows = 12 * p.bwr_ri;          // default variant; the launcher re-plans for the variant it runs
+    p.sms = sms;
+    p.n_js_bwf = kMaxSplits; p.js_len_bwf = 0;
     // ---- backward column pass (grad_mu): a CTA owns bwc_cols columns and a range of is_len rows
     p.bwc_rj = p.dpt >= 16 ? 2 : (p.dpt >= 8 ? 4 : 8);
     p.bwc_cols = kBwdWarps * p.bwc_rj;
     p.bwc_it = 2048 / dp; if (p.bwc_it < 4) p.bwc_it = 4; if (p.bwc_it > 16) p.bwc_it = 16;
     p.n_cb = p.bg_pad / p.bwc_cols;
-    {
-        const int slots = sms * 2;
-        const int min_len = p.bwc_it * 4;
-        int max_is = p.bl_pad / min_len; if (max_is < 1) max_is = 1;
-        int want = (slots * 8 + p.n_cb - 1) / p.n_cb;
-        if (want < 1) want = 1; if (want > max_is) want = max_is;
-        p.is_len = (int)round_up((p.bl_pad + want - 1) / want, p.bwc_it);
-        p.n_is = (p.bl_pad + p.is_len - 1) / p.is_len;
-    }
+    choose_splits(p.n_cb, sms * 2, p.bl_pad, p.bwc_it, 4, p.n_is, p.is_len);
 
     // ---- workspace
     size_t off = 0;

@@ -1,0 +1,63 @@
+"""Sweep the fused-backward kernel variants (tcelbo_set_tuning) on one GPU and print per-variant times.
+
+    python tools/tune_bwd.py [--batch 8192] [--zdim 128] [--variants 0,1,2,...]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from intro_tc_vae_b200 import _lib, ops  # noqa: F401  (registers torch.ops.tcelbo)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--zdim", type=int, default=128)
+    ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,8,9,10")
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    B, D, N = args.batch, args.zdim, 16704
+    g = torch.Generator().manual_seed(1234)
+    mu = torch.randn(B, D, generator=g).to(dev)
+    lv = (-2.0 + torch.randn(B, D, generator=g)).to(dev)
+    z = mu + torch.randn(B, D, generator=g).to(dev) * torch.exp(0.5 * lv)
+    flags = _lib.EST_MSS | _lib.VAR_ROW | _lib.SAVE_FOR_BACKWARD
+    lq, lqp, ws = torch.ops.tcelbo.tc_forward(z, mu, lv, 0, N, flags)
+    gj = torch.full((B,), 0.5 / B, device=dev)
+    gp = -gj
+    ref = None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for v in [int(x) for x in args.variants.split(",")]:
+        _lib.check(lib.tcelbo_set_tuning(b"bwd_variant", v), "set_tuning")
+        try:
+            for _ in range(2):
+                out = torch.ops.tcelbo.tc_backward(z, mu, lv, 0, N, flags, gj, gp, ws)
+            torch.cuda.synchronize()
+        except Exception as e:                                  # a variant that cannot launch (smem / regs)
+            print(f"variant {v:2d}: FAILED {e}")
+            continue
+        ts = []
+        for _ in range(args.reps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = torch.ops.tcelbo.tc_backward(z, mu, lv, 0, N, flags, gj, gp, ws)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        if ref is None:
+            ref = [t.clone() for t in out]
+            err = 0.0
+        else:
+            err = max(((a - b).abs().max() / b.abs().max()).item() for a, b in zip(out, ref))
+        ts.sort()
+        print(f"variant {v:2d}: backward total {ts[len(ts)//2]:.3f} ms (min {ts[0]:.3f})  max rel diff vs first {err:.1e}")
+    lib.tcelbo_set_tuning(b"bwd_variant", -1)
+
+
+if __name__ == "__main__":
+    main()
