@@ -119,6 +119,72 @@ __device__ __forceinline__ void bwd_rows_phased(const u64 (&mu2)[NP], const u64 
     }
 }
 
+// All JS columns of one staging sub-tile for this warp's RI rows.  Templated on the special-tile case so
+// the GV unrolled columns form ONE basic block and independent (row, column) chains can be interleaved.
+template <int DPT, int RI, int JS_, bool PHASED, bool kSpecial>
+__device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, const float* __restrict__ gq, float* __restrict__ gst,
+                                            int sub, int lane, int jt0, int i_glob0, const Weights& w,
+                                            const u64 (&zs2)[RI][BwdGeom<DPT, JS_>::NP], const u64 (&ns2)[RI][BwdGeom<DPT, JS_>::NP],
+                                            const float (&qmx)[RI][2 * BwdGeom<DPT, JS_>::NP], const u64 (&gps2)[RI][BwdGeom<DPT, JS_>::NP],
+                                            u64 (&A2)[RI][BwdGeom<DPT, JS_>::NP], u64 (&CR2)[RI][BwdGeom<DPT, JS_>::NP]) {
+    using GEO = BwdGeom<DPT, JS_>;
+    constexpr int VEC = GEO::VEC, NCH = GEO::NCH, DP = GEO::DP, CH = GEO::CH, JT = GEO::JT, JS = GEO::JS, GV = GEO::GV, NP = GEO::NP;
+    constexpr int RG = (RI % 2 == 0) ? 2 : 1;
+#pragma unroll 1
+    for (int g0 = 0; g0 < JS; g0 += GV) {
+        float gqv[RI][GV];
+#pragma unroll
+        for (int r = 0; r < RI; ++r) VecLd<GV>::ld(gq + r * JT + sub + g0, gqv[r]);
+#pragma unroll
+        for (int u = 0; u < GV; ++u) {
+            const int jj = sub + g0 + u;
+            u64 mu2[NP], G2[NP];
+            {
+                float vm[DPT];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    float v[VEC];
+                    VecLd<VEC>::ld(tile + jj * DP + c * CH + VEC * lane, v);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) vm[c * VEC + e] = v[e];
+                }
+#pragma unroll
+                for (int p = 0; p < NP; ++p) { mu2[p] = pack2(vm[2 * p], DPT >= 2 ? vm[(2 * p + 1) % DPT] : 0.0f); G2[p] = 0ull; }
+            }
+            float rho[RI];
+#pragma unroll
+            for (int r = 0; r < RI; ++r) {
+                rho[r] = 1.0f;
+                if (kSpecial) { float l2; weight_of(w, i_glob0 + r, jt0 + jj, rho[r], l2); }
+            }
+            if (PHASED) {
+#pragma unroll
+                for (int rg = 0; rg < RI; rg += RG)
+                    bwd_rows_phased<NP, RG, kSpecial>(mu2, &zs2[rg], &ns2[rg], &qmx[rg], &gps2[rg], &gqv[rg][u], GV, &rho[rg],
+                                                      &A2[rg], &CR2[rg], G2);
+            } else {
+#pragma unroll
+                for (int r = 0; r < RI; ++r)
+                    bwd_pairs<NP, kSpecial>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], rho[r], A2[r], CR2[r], G2);
+            }
+            // warp-partial column gradient -> staging buffer [warp][column][dim]
+            float vg[DPT];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                float lo, hi; unpack2(G2[p], lo, hi);
+                vg[2 * p % DPT] = lo; if (DPT >= 2) vg[(2 * p + 1) % DPT] = hi;
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float v[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v[e] = vg[c * VEC + e];
+                VecLd<VEC>::st(gst + (g0 + u) * DP + c * CH + VEC * lane, v);
+            }
+        }
+    }
+}
+
 template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED>
 __global__ void __launch_bounds__(NW * 32, MINB)
 tc_bwd_fused_kernel(const BwdFusedArgs a) {
@@ -254,69 +320,8 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
             const int b = k & 1;
             if (k >= 2) mbar_wait(&g_empty[b], ((k >> 1) - 1) & 1);           // everyone finished reducing sub-tile k-2
             float* gst = gstage + (size_t)b * GST + (size_t)warp * JS * DP;
-#pragma unroll 1
-            for (int g0 = 0; g0 < JS; g0 += GV) {
-                float gqv[RI][GV];
-#pragma unroll
-                for (int r = 0; r < RI; ++r) VecLd<GV>::ld(gq + r * JT + sub + g0, gqv[r]);
-#pragma unroll
-                for (int u = 0; u < GV; ++u) {
-                    const int jj = sub + g0 + u;
-                    u64 mu2[NP], G2[NP];
-                    {
-                        float vm[DPT];
-#pragma unroll
-                        for (int c = 0; c < NCH; ++c) {
-                            float v[VEC];
-                            VecLd<VEC>::ld(tile + jj * DP + c * CH + VEC * lane, v);
-#pragma unroll
-                            for (int e = 0; e < VEC; ++e) vm[c * VEC + e] = v[e];
-                        }
-#pragma unroll
-                        for (int p = 0; p < NP; ++p) { mu2[p] = pack2(vm[2 * p], DPT >= 2 ? vm[(2 * p + 1) % DPT] : 0.0f); G2[p] = 0ull; }
-                    }
-                    if (special) {
-                        float rho[RI];
-#pragma unroll
-                        for (int r = 0; r < RI; ++r) { float l2; weight_of(a.w, a.row_offset + row0 + r, jt0 + jj, rho[r], l2); }
-                        if (PHASED) {
-#pragma unroll
-                            for (int rg = 0; rg < RI; rg += RG)
-                                bwd_rows_phased<NP, RG, true>(mu2, &zs2[rg], &ns2[rg], &qmx[rg], &gps2[rg], &gqv[rg][u], GV, &rho[rg],
-                                                              &A2[rg], &CR2[rg], G2);
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < RI; ++r)
-                                bwd_pairs<NP, true>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], rho[r], A2[r], CR2[r], G2);
-                        }
-                    } else {
-                        if (PHASED) {
-#pragma unroll
-                            for (int rg = 0; rg < RI; rg += RG)
-                                bwd_rows_phased<NP, RG, false>(mu2, &zs2[rg], &ns2[rg], &qmx[rg], &gps2[rg], &gqv[rg][u], GV, nullptr,
-                                                               &A2[rg], &CR2[rg], G2);
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < RI; ++r)
-                                bwd_pairs<NP, false>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], 1.0f, A2[r], CR2[r], G2);
-                        }
-                    }
-                    // warp-partial column gradient -> staging buffer [warp][column][dim]
-                    float vg[DPT];
-#pragma unroll
-                    for (int p = 0; p < NP; ++p) {
-                        float lo, hi; unpack2(G2[p], lo, hi);
-                        vg[2 * p % DPT] = lo; if (DPT >= 2) vg[(2 * p + 1) % DPT] = hi;
-                    }
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        float v[VEC];
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) v[e] = vg[c * VEC + e];
-                        VecLd<VEC>::st(gst + (g0 + u) * DP + c * CH + VEC * lane, v);
-                    }
-                }
-            }
+if (special) bwd_subtile<DPT, RI, JS_, PHASED, true >(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
+            else         bwd_subtile<DPT, RI, JS_, PHASED, false>(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
             __syncwarp();
             if (lane == 0) mbar_arrive(&g_full[b]);
             if (k >= 1) reduce_share(k - 1, prev_col0);                      // the other buffer: its writers are long done
