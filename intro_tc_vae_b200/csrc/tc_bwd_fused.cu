@@ -423,11 +423,12 @@ cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out
                 case 4:  return launch_bwd_fused_t<4, 2, 8, 3, 4, false>(p, a, n_js_out, st);
                 case 5:  return launch_bwd_fused_t<4, 2, 8, 3, 4, true >(p, a, n_js_out, st);
                 case 6:  return launch_bwd_fused_t<4, 2, 16, 1, 8, true >(p, a, n_js_out, st);
-                case 7:  return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);
+                case 7:  return launch_bwd_fused_t<4, 3, 8, 2, 8, true >(p, a, n_js_out, st);
                 case 8:  return launch_bwd_fused_t<4, 2, 12, 2, 4, true >(p, a, n_js_out, st);
                 case 9:  return launch_bwd_fused_t<4, 4, 16, 1, 8, true >(p, a, n_js_out, st);
                 case 10: return launch_bwd_fused_t<4, 2, 16, 2, 4, true >(p, a, n_js_out, st);
-                default: return launch_bwd_fused_t<4, 4, 12, 1, 8, false>(p, a, n_js_out, st);
+                case 0:  return launch_bwd_fused_t<4, 4, 12, 1, 8, false>(p, a, n_js_out, st);
+                default: return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);   // best of the sweep in profiles/
             }
         case 8:  return launch_bwd_fused_t<8, 2, 12, 1, 4, false>(p, a, n_js_out, st);
         case 16: return launch_bwd_fused_t<16, 1, 12, 1, 2, false>(p, a, n_js_out, st);
