@@ -270,22 +270,27 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernels, timed live with CUDA events on the launching stream
     roof = None
-    if rank == 0:
-        cur = torch.cuda.current_stream(dev)
-        kern_ms = {}
-        for kid, name in ((1, "tc_fwd_kernel"), (2, "tc_bwd_row_kernel"), (3, "tc_bwd_col_kernel")):
-            ev0 = torch.cuda.Event(enable_timing=True)
-            ev1 = torch.cuda.Event(enable_timing=True)
-            ev0.record(cur); ev1.record(cur)               # materialise the underlying cudaEvent_t handles
-            ts = []
-            for k in range(min(args.steps, 5)):
-                flush_buf.fill_(k)
+    # every rank runs these steps (they contain the collectives); only rank 0 brackets its kernels with events
+    cur = torch.cuda.current_stream(dev)
+    kern_ms = {}
+    for kid, name in ((1, "tc_fwd_kernel"), (2, "tc_bwd_fused_kernel")):
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record(cur); ev1.record(cur)               # materialise the underlying cudaEvent_t handles
+        ts = []
+        for k in range(min(args.steps, 5)):
+            flush_buf.fill_(k)
+            if rank == 0:
                 _lib.check(lib.tcelbo_profile_events(kid, ev0.cuda_event, ev1.cuda_event), "profile_events")
-                step(mu, lv, eps)
-                torch.cuda.synchronize()
+            step(mu, lv, eps)
+            torch.cuda.synchronize()
+            if rank == 0:
                 lib.tcelbo_profile_events(0, None, None)
                 ts.append(ev0.elapsed_time(ev1))
+        if rank == 0:
             kern_ms[name] = sum(ts) / len(ts)
+    barrier()
+    if rank == 0:
         # SFU saturation probe in the same job (empirical ex2 peak)
         scratch = torch.zeros(16, device=dev)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
