@@ -88,7 +88,6 @@ int check_common(const float* z, const float* mu_all, const float* logvar, int b
     if (dataset_size < 1) return fail(TCELBO_ERR_INVALID, "dataset_size must be positive");
     if (ldz < d || ldmu < d || ldlv < d) return fail(TCELBO_ERR_INVALID, "row pitch smaller than d");
     if (d > 512) return fail(TCELBO_ERR_UNSUPPORTED, "d = %d > 512 is outside the built kernels", d);
-    if (flags & TCELBO_VAR_COL) return fail(TCELBO_ERR_UNSUPPORTED, "TCELBO_VAR_COL is not built yet");
     return TCELBO_OK;
 }
 
@@ -134,8 +133,12 @@ int tcelbo_forward(const float* z, int64_t ldz, const float* mu_all, int64_t ldm
     float* Spart = at<float>(workspace, p.off_scratch);
     float* Jpart = Spart + (size_t)p.n_js_fwd * p.bl_pad * p.dp;
 
-    if ((e = launch_col_prep(mu_all, ldmu, p, mu_pad, st)) != cudaSuccess) return fail_cuda(e, "col_prep");
-    if ((e = launch_row_prep(z, ldz, logvar, ldlv, p, zs, ns, qmax, shift, vr, st)) != cudaSuccess) return fail_cuda(e, "row_prep");
+    if (p.var_col) {
+        if ((e = launch_colvar_prep(z, ldz, mu_all, ldmu, logvar, ldlv, p, mu_pad, zs, shift, st)) != cudaSuccess) return fail_cuda(e, "colvar_prep");
+    } else {
+        if ((e = launch_col_prep(mu_all, ldmu, p, mu_pad, st)) != cudaSuccess) return fail_cuda(e, "col_prep");
+        if ((e = launch_row_prep(z, ldz, logvar, ldlv, p, zs, ns, qmax, shift, vr, st)) != cudaSuccess) return fail_cuda(e, "row_prep");
+    }
 
     FwdArgs fa;
     fa.zs = zs; fa.ns = ns; fa.qmax = qmax; fa.mu_pad = mu_pad;
@@ -143,13 +146,18 @@ int tcelbo_forward(const float* z, int64_t ldz, const float* mu_all, int64_t ldm
     fa.Spart = Spart; fa.Jpart = Jpart;
     fa.b_loc = b_loc; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.row_offset = row_offset; fa.js_len = p.js_len_fwd;
     fa.w = w;
-    if ((e = launch_fwd(p, fa, st)) != cudaSuccess) return fail_cuda(e, "tc_fwd");
+    int n_js_used = p.n_js_fwd;
+    if (p.var_col) {
+        if ((e = launch_fwd_colvar(p, fa, &n_js_used, st)) != cudaSuccess) return fail_cuda(e, "tc_fwd_colvar");
+    } else {
+        if ((e = launch_fwd(p, fa, st)) != cudaSuccess) return fail_cuda(e, "tc_fwd");
+    }
 
     FinArgs fin;
     fin.Spart = Spart; fin.Jpart = Jpart; fin.shift = shift;
     fin.S = at<float>(workspace, p.off_S); fin.J2 = at<float>(workspace, p.off_J2);
     fin.log_qz = log_qz; fin.log_qz_prod = log_qz_prod;
-    fin.b_loc = b_loc; fin.bl_pad = p.bl_pad; fin.d = d; fin.dp = p.dp; fin.n_js = p.n_js_fwd; fin.lw_u = w.lw_u;
+    fin.b_loc = b_loc; fin.bl_pad = p.bl_pad; fin.d = d; fin.dp = p.dp; fin.n_js = n_js_used; fin.lw_u = w.lw_u;
     if ((e = launch_fwd_finalize(p, fin, st)) != cudaSuccess) return fail_cuda(e, "fwd_finalize");
     return TCELBO_OK;
 }
@@ -190,13 +198,32 @@ int tcelbo_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ld
 
     if ((e = launch_bwd_prep(p, g_log_qz, g_log_qz_prod, S, gps, gj, st)) != cudaSuccess) return fail_cuda(e, "bwd_prep");
 
+    if (p.var_col) {
+        float* Gmu = Gpart;
+        float* Glv = Gpart + (size_t)p.bg_pad * p.dp;
+        if ((e = cudaMemsetAsync(Gmu, 0, 2 * (size_t)p.bg_pad * p.dp * sizeof(float), st)) != cudaSuccess) return fail_cuda(e, "memset");
+        BwdFusedArgs ua;
+        ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
+        ua.s2 = s2; ua.ld_s2 = p.ld_s2; ua.Apart = Apart; ua.CRpart = CRpart; ua.Gacc = Gmu; ua.Gacc2 = Glv;
+        ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = 0; ua.w = w;
+        int n_js_cv = 1;
+        if ((e = launch_bwd_colvar(p, ua, &n_js_cv, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_colvar");
+        BwdFinArgs fa;
+        fa.Apart = Apart; fa.CRpart = CRpart; fa.Gpart = Gmu; fa.ns = ns; fa.vr = vr;
+        fa.grad_z = grad_z; fa.ldgz = ldgz; fa.grad_lv = grad_logvar; fa.ldglv = ldglv; fa.grad_mu = grad_mu_all; fa.ldgmu = ldgmu;
+        fa.b_loc = b_loc; fa.b_glob = b_glob; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.d = d; fa.dp = p.dp;
+        fa.n_js = n_js_cv; fa.n_is = 1;
+        if ((e = launch_bwd_colvar_finalize(p, fa, mu_pad, Glv, st)) != cudaSuccess) return fail_cuda(e, "bwd_colvar_finalize");
+        return TCELBO_OK;
+    }
+
     static const bool two_pass = (std::getenv("TCELBO_BWD_TWOPASS") != nullptr);   // A/B switch: older two-sweep backward
     if (!two_pass) {
         // single fused sweep: row-local sums in registers, column sums via smem staging + red.global
         if ((e = cudaMemsetAsync(Gpart, 0, (size_t)p.bg_pad * p.dp * sizeof(float), st)) != cudaSuccess) return fail_cuda(e, "memset");
         BwdFusedArgs ua;
         ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
-        ua.s2 = s2; ua.ld_s2 = p.ld_s2; ua.Apart = Apart; ua.CRpart = CRpart; ua.Gacc = Gpart;
+        ua.s2 = s2; ua.ld_s2 = p.ld_s2; ua.Apart = Apart; ua.CRpart = CRpart; ua.Gacc = Gpart; ua.Gacc2 = nullptr;
         ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = 0; ua.w = w;
         int n_js_fused = 1;
         if ((e = launch_bwd_fused(p, ua, &n_js_fused, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");

@@ -51,6 +51,7 @@ struct BwdFusedArgs {
     const float* s2; int64_t ld_s2;
     float* Apart; float* CRpart;                                             // [n_js][bl_pad][dp]
     float* Gacc;                                                             // [bg_pad][dp], zeroed by the caller
+    float* Gacc2;                                                            // column-variance variant: logvar column sums
     int b_loc, bl_pad, bg_pad, row_offset, js_len;
     Weights w;
 };
@@ -74,6 +75,12 @@ cudaError_t launch_bwd_col(const Plan& p, const BwdColArgs& a, cudaStream_t st);
 cudaError_t launch_bwd_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st);
 cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out, cudaStream_t st);
 void set_bwd_variant(int v);
+// column-variance ("full" path) variant, tc_colvar.cu
+cudaError_t launch_colvar_prep(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* lv_all, int64_t ldlv,
+                               const Plan& p, float* colpack, float* zpad, float* shift, cudaStream_t st);
+cudaError_t launch_fwd_colvar(const Plan& p, const FwdArgs& a, int* n_js_out, cudaStream_t st);
+cudaError_t launch_bwd_colvar(const Plan& p, const BwdFusedArgs& a, int* n_js_out, cudaStream_t st);
+cudaError_t launch_bwd_colvar_finalize(const Plan& p, const BwdFinArgs& a, const float* colpack, const float* Glv, cudaStream_t st);
 cudaError_t launch_bwd_fused_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st);
 
 }  // namespace tcelbo

@@ -34,7 +34,7 @@ struct Plan {
     size_t total_bytes;                                           // forward workspace (read-only in backward)
     // backward scratch (its own buffer, so the forward workspace stays immutable and backward can be re-run)
     size_t boff_gps, boff_gj, boff_A, boff_CR, boff_G, bwd_bytes;
-    bool save;
+    bool save, var_col;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -73,6 +73,7 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.jt = kTileFloats / dp;                                   // 128 .. 8
     if (p.jt > 32) p.jt = 32;
     p.save = (flags & 4u) != 0;
+    p.var_col = (flags & 2u) != 0;
 
     // ---- forward: a CTA owns fwd_rows rows and a contiguous range of js_len columns
     p.fwd_rows = kFwdWarps * (32 / p.dpt);
@@ -98,7 +99,7 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     size_t off = 0;
     const size_t row_arr = (size_t)p.bl_pad * dp * sizeof(float);
     const size_t col_arr = (size_t)p.bg_pad * dp * sizeof(float);
-    p.off_mu = off;    off = align256(off + col_arr);
+    p.off_mu = off;    off = align256(off + (p.var_col ? 3 : 1) * col_arr);          // column operand(s), padded
     p.off_zs = off;    off = align256(off + row_arr);
     p.off_ns = off;    off = align256(off + row_arr);
     p.off_qmax = off;  off = align256(off + row_arr);
@@ -118,7 +119,7 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     const int n_js_max = p.n_js_bwr > p.n_js_bwf ? p.n_js_bwr : p.n_js_bwf;
     p.boff_A = b;   b = align256(b + (size_t)n_js_max * row_arr);
     p.boff_CR = b;  b = align256(b + (size_t)n_js_max * row_arr);
-    p.boff_G = b;   b = align256(b + (size_t)p.n_is * col_arr);
+    p.boff_G = b;   b = align256(b + (size_t)(p.n_is > 2 ? p.n_is : 2) * col_arr);
     p.bwd_bytes = b;
     return true;
 }

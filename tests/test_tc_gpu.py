@@ -291,3 +291,102 @@ def test_reparameterize_consumes_rng_like_reference():
     std = torch.exp(0.5 * lv)
     ref = mu + torch.randn_like(std) * std
     assert relerr(z, ref) < 1e-6
+
+
+class _FakeDataset:
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+
+class _FakeSolver:
+    """Duck-typed solver: the TC loss methods only read beta_kl, dataset and write_scalar (solvers/tc.py:69-144)."""
+    process_group = None
+
+    def __init__(self, n, beta):
+        self.dataset = _FakeDataset(n)
+        self.beta_kl = beta
+        self.written = []
+
+    def write_scalar(self, it, tag, value):
+        self.written.append((tag, float(value)))
+
+
+@pytest.mark.parametrize("name", FINITE_CASES)
+def test_golden_column_variance_and_full_decomposition(golden, name):
+    """solvers/tc.py:91-144 ('full' MI + beta*TC + dim-KL path): column-variance density + MSS, through the
+    solver mixin, against the live reference's outputs and autograd gradients."""
+    from intro_tc_vae_b200.solvers.tc import TCLossMixin
+    ops = _ops()
+    case = CASES[name]
+    N, beta = case["N"], case["beta"]
+    pre = f"{name}/f32/"
+    mu, lv, eps, _ = _cuda_leafs(case)
+    z = ops.reparameterize(mu, lv, eps)
+    prod, joint = ops.tc_terms(z, mu, lv, N, "mss", "col")
+    assert relerr(prod, golden[pre + "varj_log_qz_prod"]) < LOSS_RTOL
+    assert relerr(joint, golden[pre + "varj_log_qz"]) < LOSS_RTOL
+    prod_w, joint_w = ops.tc_terms(z, mu, lv, N, "mws", "col")
+    assert relerr(prod_w, golden[pre + "varj_mws_log_qz_prod"]) < LOSS_RTOL
+    assert relerr(joint_w, golden[pre + "varj_mws_log_qz"]) < LOSS_RTOL
+
+    solver = _FakeSolver(N, beta)
+    full = TCLossMixin._compute_kl_loss_full(solver, z, mu, lv, "mean", None, True)
+    ref = float(golden[pre + "full_mean"])
+    scale = max(1.0, beta * np.abs(golden[pre + "varj_log_qz_prod"]).mean() / abs(ref))
+    assert abs(full.item() - ref) < LOSS_RTOL * abs(ref) * scale
+    assert solver.written and solver.written[0][0] == "kl_loss_unscaled"
+    full.backward()
+    assert relerr(mu.grad, golden[pre + "full_mean_dmu"]) < GRAD_RTOL
+    assert relerr(lv.grad, golden[pre + "full_mean_dlv"]) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("name", ["base_B64_D128", "stress_B64_D128", "tiny_B3_D128"])
+def test_solver_mixin_simple_path(golden, name):
+    """compute_kl_loss -> _compute_kl_loss_simple: (beta-1)*TC + KL, beta override, reduce modes, KL-only logging."""
+    from intro_tc_vae_b200.solvers.tc import TCLossMixin
+    ops = _ops()
+    case = CASES[name]
+    N, beta = case["N"], case["beta"]
+    pre = f"{name}/f32/"
+    mu, lv, eps, _ = _cuda_leafs(case)
+    z = ops.reparameterize(mu, lv, eps)
+    solver = _FakeSolver(N, beta)
+    loss = TCLossMixin.compute_kl_loss(solver, z, mu, lv, write=True)
+    ref = float(golden[pre + "simple_mean"])
+    scale = max(1.0, beta * np.abs(golden[pre + "log_qz_prod"]).mean() / abs(ref))
+    assert loss.dim() == 0 and abs(loss.item() - ref) < LOSS_RTOL * abs(ref) * scale
+    assert solver.written[0][0] == "kl_loss_unscaled"
+    assert abs(solver.written[0][1] - float(golden[pre + "kl"].mean())) < LOSS_RTOL * abs(float(golden[pre + "kl"].mean()))
+    per = TCLossMixin.compute_kl_loss(solver, z, mu, lv, reduce="none", beta=float(beta))
+    assert per.shape == (case["B"],)
+    ref_none = golden[pre + "simple_none"]
+    assert relerr(per, ref_none) < LOSS_RTOL * max(1.0, beta * np.abs(golden[pre + "log_qz_prod"]).max() / np.abs(ref_none).max())
+    zero_beta = TCLossMixin.compute_kl_loss(solver, z, mu, lv, beta=0.0)          # an explicit 0.0 is honoured
+    tc = ops.total_correlation(z, mu, lv, N)
+    kl = ops.kl_divergence(lv, mu, reduce="mean")
+    assert abs(zero_beta.item() - (-tc + kl).item()) < 1e-3 * max(1.0, abs(zero_beta.item()))
+
+
+@pytest.mark.parametrize("B,D", [(256, 128), (96, 32), (48, 256)])
+def test_column_variance_seeded_against_cpu_oracle(B, D):
+    ops = _ops()
+    N, beta = 16704, 4.0
+    mu_c, lv_c, eps_c = _random_latents(B, D, "base", seed=21)
+    mu_o, lv_o = mu_c.clone().requires_grad_(True), lv_c.clone().requires_grad_(True)
+    z_o = O.reparameterize(mu_o, lv_o, eps_c)
+    loss_o, mi_o, tc_o, dk_o = O.kl_loss_full(z_o, mu_o, lv_o, N, beta, "mean")
+    loss_o.backward()
+    mu = mu_c.cuda().requires_grad_(True)
+    lv = lv_c.cuda().requires_grad_(True)
+    z = ops.reparameterize(mu, lv, eps_c.cuda())
+    prod, joint = ops.tc_terms(z, mu, lv, N, "mss", "col")
+    condx = ops.row_log_density(z, mu, lv)
+    pz = ops.row_log_density(z)
+    loss = (condx - joint).mean() + beta * (joint - prod).mean() + (prod - pz).mean()
+    loss.backward()
+    assert abs(loss.item() - loss_o.item()) < LOSS_RTOL * beta * prod.abs().mean().item()
+    assert relerr(mu.grad, mu_o.grad) < GRAD_RTOL
+    assert relerr(lv.grad, lv_o.grad) < GRAD_RTOL
