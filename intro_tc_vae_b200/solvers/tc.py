@@ -31,7 +31,7 @@ class TCLossMixin:
             beta = self.beta_kl
         dataset_size = len(self.dataset)
         kl_loss = ops.kl_divergence(logvar, mu, reduce=reduce)
-        tc = ops.total_correlation(z, mu, logvar, dataset_size, reduce=reduce, group=self.process_group)
+        tc = ops.total_correlation(z, mu, logvar, dataset_size, reduce=reduce, group=getattr(self, "process_group", None))
         if write:
             self.write_scalar(SingletonWriter().cur_iter, "kl_loss_unscaled", kl_loss)   # KL only, as in the reference
         return (beta - 1.0) * tc + kl_loss
