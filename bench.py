@@ -189,9 +189,8 @@ def run_ours(args):
         mu_t.grad = None
         lv_t.grad = None
         z = ops.reparameterize(mu_t, lv_t, eps_t)
-        kl = ops.kl_divergence(lv_t, mu_t, reduce="mean")
-        tc = ops.total_correlation(z, mu_t, lv_t, N, reduce="mean", group=group)
-        loss = (BETA - 1.0) * tc + kl
+        # compute_kl_loss of solvers/tc.py:69-89 as one fused op (per-sample (beta-1)*tc + kl), mean-reduced
+        loss = ops.kl_tc_loss_terms(z, mu_t, lv_t, N, BETA, "mss", group)[0].mean()
         loss.backward()
         return loss
 

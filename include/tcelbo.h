@@ -106,6 +106,25 @@ int tcelbo_backward(const float* z, int64_t ldz,
                     const void* workspace, size_t workspace_bytes,
                     void* scratch, size_t scratch_bytes, void* stream);
 
+/*
+ * Fused compute_kl_loss of TCSovler._compute_kl_loss_simple (solvers/tc.py:69-89), row-variance density:
+ *   kl_rows[i]   = -0.5 * sum_d (1 + logvar - exp(logvar) - mu^2)                      (ops.py:161-163)
+ *   loss_rows[i] = (beta - 1) * (log_qz[i] - log_qz_prod[i]) + kl_rows[i]
+ * Same arguments as tcelbo_forward / tcelbo_backward; mu of this rank's rows is read from
+ * mu_all[row_offset .. row_offset + b_loc).  The backward takes dLoss/dloss_rows (required) and optionally
+ * dLoss/dkl_rows, dLoss/dlog_qz, dLoss/dlog_qz_prod (NULL = zero); the KL gradient is added to grad_logvar and to
+ * this rank's rows of grad_mu_all, so no separate KL kernels or elementwise combine kernels are launched.
+ */
+int tcelbo_klloss_forward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                          int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags, float beta,
+                          float* loss_rows, float* kl_rows, float* log_qz, float* log_qz_prod,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int tcelbo_klloss_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                           int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags, float beta,
+                           const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
+                           float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
+                           const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream);
+
 /* kl_rows[i] = -0.5 * sum_d (1 + logvar - exp(logvar) - mu^2)   (ops.py:161-163; argument order logvar, mu) */
 int tcelbo_kl_forward(const float* logvar, int64_t ldlv, const float* mu, int64_t ldmu,
                       int b, int d, float* kl_rows, void* stream);

@@ -111,15 +111,25 @@ size_t tcelbo_backward_scratch_bytes(int b_loc, int b_glob, int d, uint32_t flag
     return p.bwd_bytes;
 }
 
-int tcelbo_forward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
-                   int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
-                   float* log_qz, float* log_qz_prod, void* workspace, size_t workspace_bytes, void* stream) {
+// ---- shared implementation of the plain and the loss-fused entry points ---------------------------------
+struct LossFusion {            // solvers/tc.py:83-89 folded into the finalize kernels (null pointers: plain op)
+    float beta = 1.0f;
+    float* loss_rows = nullptr; float* kl_rows = nullptr;                 // forward outputs
+    const float* g_loss = nullptr; const float* g_kl = nullptr;           // backward inputs
+    bool on = false;
+};
+
+static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                        int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
+                        float* log_qz, float* log_qz_prod, const LossFusion& lf,
+                        void* workspace, size_t workspace_bytes, void* stream) {
     if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv)) return rc;
     if (!log_qz || !log_qz_prod) return fail(TCELBO_ERR_INVALID, "null output pointer");
     Plan p;
     if (!make_plan(p, b_loc, b_glob, d, flags, sm_count())) return fail(TCELBO_ERR_INVALID, "cannot plan this shape");
     if (!workspace || workspace_bytes < p.total_bytes || !aligned256(workspace))
         return fail(TCELBO_ERR_WORKSPACE, "workspace must be 256-byte aligned and at least %zu bytes (got %zu)", p.total_bytes, workspace_bytes);
+    if (lf.on && p.var_col) return fail(TCELBO_ERR_INVALID, "the fused (beta-1)*TC + KL loss uses the row-variance density (solvers/tc.py:69-89)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Weights w = make_weights(b_glob, dataset_size, flags);
     cudaError_t e;
@@ -158,18 +168,24 @@ int tcelbo_forward(const float* z, int64_t ldz, const float* mu_all, int64_t ldm
     fin.S = at<float>(workspace, p.off_S); fin.J2 = at<float>(workspace, p.off_J2);
     fin.log_qz = log_qz; fin.log_qz_prod = log_qz_prod;
     fin.b_loc = b_loc; fin.bl_pad = p.bl_pad; fin.d = d; fin.dp = p.dp; fin.n_js = n_js_used; fin.lw_u = w.lw_u;
+    fin.lv = nullptr; fin.ldlv = 0; fin.mu_loc = nullptr; fin.ldmu = 0; fin.beta = lf.beta; fin.loss_rows = nullptr; fin.kl_rows = nullptr;
+    if (lf.on) {
+        fin.lv = logvar; fin.ldlv = ldlv; fin.mu_loc = mu_all + (int64_t)row_offset * ldmu; fin.ldmu = ldmu;
+        fin.loss_rows = lf.loss_rows; fin.kl_rows = lf.kl_rows;
+    }
     if ((e = launch_fwd_finalize(p, fin, st)) != cudaSuccess) return fail_cuda(e, "fwd_finalize");
     return TCELBO_OK;
 }
 
-int tcelbo_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
-                    int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
-                    const float* g_log_qz, const float* g_log_qz_prod,
-                    float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
-                    const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream) {
+static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                         int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
+                         const float* g_log_qz, const float* g_log_qz_prod, const LossFusion& lf,
+                         float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
+                         const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream) {
     if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv)) return rc;
     if (!(flags & TCELBO_SAVE_FOR_BACKWARD)) return fail(TCELBO_ERR_INVALID, "backward needs the workspace of a forward run with TCELBO_SAVE_FOR_BACKWARD");
-    if (!g_log_qz || !g_log_qz_prod || !grad_z || !grad_mu_all || !grad_logvar) return fail(TCELBO_ERR_INVALID, "null gradient pointer");
+    if (!grad_z || !grad_mu_all || !grad_logvar) return fail(TCELBO_ERR_INVALID, "null gradient pointer");
+    if (!lf.on && (!g_log_qz || !g_log_qz_prod)) return fail(TCELBO_ERR_INVALID, "null upstream gradient pointer");
     if (ldgz < d || ldgmu < d || ldglv < d) return fail(TCELBO_ERR_INVALID, "gradient row pitch smaller than d");
     Plan p;
     if (!make_plan(p, b_loc, b_glob, d, flags, sm_count())) return fail(TCELBO_ERR_INVALID, "cannot plan this shape");
@@ -177,6 +193,7 @@ int tcelbo_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ld
         return fail(TCELBO_ERR_WORKSPACE, "workspace must be the %zu-byte buffer forward wrote (got %zu)", p.total_bytes, workspace_bytes);
     if (!scratch || scratch_bytes < p.bwd_bytes || !aligned256(scratch))
         return fail(TCELBO_ERR_WORKSPACE, "scratch must be 256-byte aligned and at least %zu bytes (got %zu)", p.bwd_bytes, scratch_bytes);
+    if (lf.on && p.var_col) return fail(TCELBO_ERR_INVALID, "the fused loss uses the row-variance density");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Weights w = make_weights(b_glob, dataset_size, flags);
     cudaError_t e;
@@ -192,69 +209,96 @@ int tcelbo_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ld
     const float* s2 = at<float>(wsm, p.off_s2);
     float* gps = at<float>(scratch, p.boff_gps);
     float* gj = at<float>(scratch, p.boff_gj);
+    float* gk = at<float>(scratch, p.boff_gk);
     float* Apart = at<float>(scratch, p.boff_A);
     float* CRpart = at<float>(scratch, p.boff_CR);
     float* Gpart = at<float>(scratch, p.boff_G);
 
-    if ((e = launch_bwd_prep(p, g_log_qz, g_log_qz_prod, S, gps, gj, st)) != cudaSuccess) return fail_cuda(e, "bwd_prep");
+    static const bool two_pass = (std::getenv("TCELBO_BWD_TWOPASS") != nullptr);   // A/B switch: older two-sweep backward
+    const bool use_fused = p.var_col || !two_pass;
+    const size_t zero_n = use_fused ? (size_t)(p.var_col ? 2 : 1) * p.bg_pad * p.dp : 0;
+    if ((e = launch_bwd_prep(p, g_log_qz, g_log_qz_prod, lf.g_loss, lf.g_kl, lf.beta, S, gps, gj, lf.on ? gk : nullptr,
+                             Gpart, zero_n, st)) != cudaSuccess) return fail_cuda(e, "bwd_prep");
+
+    BwdFinArgs fa;
+    fa.Apart = Apart; fa.CRpart = CRpart; fa.Gpart = Gpart; fa.ns = ns; fa.vr = vr;
+    fa.grad_z = grad_z; fa.ldgz = ldgz; fa.grad_lv = grad_logvar; fa.ldglv = ldglv; fa.grad_mu = grad_mu_all; fa.ldgmu = ldgmu;
+    fa.b_loc = b_loc; fa.b_glob = b_glob; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.d = d; fa.dp = p.dp;
+    fa.n_js = 1; fa.n_is = 1;
+    fa.gk = lf.on ? gk : nullptr; fa.lv = logvar; fa.ldlv = ldlv; fa.mu_all = mu_all; fa.ldmu = ldmu; fa.row_offset = row_offset;
+
+    BwdFusedArgs ua;
+    ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
+    ua.s2 = s2; ua.ld_s2 = p.ld_s2; ua.Apart = Apart; ua.CRpart = CRpart; ua.Gacc = Gpart; ua.Gacc2 = nullptr;
+    ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = 0; ua.w = w;
 
     if (p.var_col) {
-        float* Gmu = Gpart;
         float* Glv = Gpart + (size_t)p.bg_pad * p.dp;
-        if ((e = cudaMemsetAsync(Gmu, 0, 2 * (size_t)p.bg_pad * p.dp * sizeof(float), st)) != cudaSuccess) return fail_cuda(e, "memset");
-        BwdFusedArgs ua;
-        ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
-        ua.s2 = s2; ua.ld_s2 = p.ld_s2; ua.Apart = Apart; ua.CRpart = CRpart; ua.Gacc = Gmu; ua.Gacc2 = Glv;
-        ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = 0; ua.w = w;
-        int n_js_cv = 1;
-        if ((e = launch_bwd_colvar(p, ua, &n_js_cv, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_colvar");
-        BwdFinArgs fa;
-        fa.Apart = Apart; fa.CRpart = CRpart; fa.Gpart = Gmu; fa.ns = ns; fa.vr = vr;
-        fa.grad_z = grad_z; fa.ldgz = ldgz; fa.grad_lv = grad_logvar; fa.ldglv = ldglv; fa.grad_mu = grad_mu_all; fa.ldgmu = ldgmu;
-        fa.b_loc = b_loc; fa.b_glob = b_glob; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.d = d; fa.dp = p.dp;
-        fa.n_js = n_js_cv; fa.n_is = 1;
+        ua.Gacc2 = Glv;
+        if ((e = launch_bwd_colvar(p, ua, &fa.n_js, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_colvar");
         if ((e = launch_bwd_colvar_finalize(p, fa, mu_pad, Glv, st)) != cudaSuccess) return fail_cuda(e, "bwd_colvar_finalize");
         return TCELBO_OK;
     }
-
-    static const bool two_pass = (std::getenv("TCELBO_BWD_TWOPASS") != nullptr);   // A/B switch: older two-sweep backward
-    if (!two_pass) {
+    if (use_fused) {
         // single fused sweep: row-local sums in registers, column sums via smem staging + red.global
-        if ((e = cudaMemsetAsync(Gpart, 0, (size_t)p.bg_pad * p.dp * sizeof(float), st)) != cudaSuccess) return fail_cuda(e, "memset");
-        BwdFusedArgs ua;
-        ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
-        ua.s2 = s2; ua.ld_s2 = p.ld_s2; ua.Apart = Apart; ua.CRpart = CRpart; ua.Gacc = Gpart; ua.Gacc2 = nullptr;
-        ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = 0; ua.w = w;
-        int n_js_fused = 1;
-        if ((e = launch_bwd_fused(p, ua, &n_js_fused, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");
-        BwdFinArgs fa;
-        fa.Apart = Apart; fa.CRpart = CRpart; fa.Gpart = Gpart; fa.ns = ns; fa.vr = vr;
-        fa.grad_z = grad_z; fa.ldgz = ldgz; fa.grad_lv = grad_logvar; fa.ldglv = ldglv; fa.grad_mu = grad_mu_all; fa.ldgmu = ldgmu;
-        fa.b_loc = b_loc; fa.b_glob = b_glob; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.d = d; fa.dp = p.dp;
-        fa.n_js = n_js_fused; fa.n_is = 1;
+        if ((e = launch_bwd_fused(p, ua, &fa.n_js, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");
         if ((e = launch_bwd_fused_finalize(p, fa, st)) != cudaSuccess) return fail_cuda(e, "bwd_fused_finalize");
         return TCELBO_OK;
     }
+    if (lf.on) return fail(TCELBO_ERR_INVALID, "TCELBO_BWD_TWOPASS does not support the fused loss entry points");
 
     BwdRowArgs ra;
     ra.zs = zs; ra.ns = ns; ra.qmax = qmax; ra.gps = gps; ra.gj = gj; ra.J2 = J2; ra.mu_pad = mu_pad;
     ra.s2 = s2; ra.ld_s2 = p.ld_s2; ra.Apart = Apart; ra.CRpart = CRpart;
     ra.b_loc = b_loc; ra.bl_pad = p.bl_pad; ra.bg_pad = p.bg_pad; ra.row_offset = row_offset; ra.js_len = p.js_len_bwr; ra.w = w;
     if ((e = launch_bwd_row(p, ra, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_row");
-
     BwdColArgs ca;
     ca.zs = zs; ca.ns = ns; ca.qmax = qmax; ca.gps = gps; ca.gj = gj; ca.J2 = J2; ca.mu_pad = mu_pad;
     ca.s2 = s2; ca.ld_s2 = p.ld_s2; ca.Gpart = Gpart;
     ca.b_loc = b_loc; ca.bl_pad = p.bl_pad; ca.bg_pad = p.bg_pad; ca.row_offset = row_offset; ca.is_len = p.is_len; ca.w = w;
     if ((e = launch_bwd_col(p, ca, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_col");
-
-    BwdFinArgs fa;
-    fa.Apart = Apart; fa.CRpart = CRpart; fa.Gpart = Gpart; fa.ns = ns; fa.vr = vr;
-    fa.grad_z = grad_z; fa.ldgz = ldgz; fa.grad_lv = grad_logvar; fa.ldglv = ldglv; fa.grad_mu = grad_mu_all; fa.ldgmu = ldgmu;
-    fa.b_loc = b_loc; fa.b_glob = b_glob; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.d = d; fa.dp = p.dp;
     fa.n_js = p.n_js_bwr; fa.n_is = p.n_is;
     if ((e = launch_bwd_finalize(p, fa, st)) != cudaSuccess) return fail_cuda(e, "bwd_finalize");
     return TCELBO_OK;
+}
+
+int tcelbo_forward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                   int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
+                   float* log_qz, float* log_qz_prod, void* workspace, size_t workspace_bytes, void* stream) {
+    return forward_impl(z, ldz, mu_all, ldmu, logvar, ldlv, b_loc, b_glob, row_offset, d, dataset_size, flags,
+                        log_qz, log_qz_prod, LossFusion(), workspace, workspace_bytes, stream);
+}
+
+int tcelbo_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                    int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
+                    const float* g_log_qz, const float* g_log_qz_prod,
+                    float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
+                    const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream) {
+    return backward_impl(z, ldz, mu_all, ldmu, logvar, ldlv, b_loc, b_glob, row_offset, d, dataset_size, flags,
+                         g_log_qz, g_log_qz_prod, LossFusion(), grad_z, ldgz, grad_mu_all, ldgmu, grad_logvar, ldglv,
+                         workspace, workspace_bytes, scratch, scratch_bytes, stream);
+}
+
+int tcelbo_klloss_forward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                          int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags, float beta,
+                          float* loss_rows, float* kl_rows, float* log_qz, float* log_qz_prod,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    if (!loss_rows || !kl_rows) return fail(TCELBO_ERR_INVALID, "null output pointer");
+    LossFusion lf; lf.on = true; lf.beta = beta; lf.loss_rows = loss_rows; lf.kl_rows = kl_rows;
+    return forward_impl(z, ldz, mu_all, ldmu, logvar, ldlv, b_loc, b_glob, row_offset, d, dataset_size, flags,
+                        log_qz, log_qz_prod, lf, workspace, workspace_bytes, stream);
+}
+
+int tcelbo_klloss_backward(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                           int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags, float beta,
+                           const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
+                           float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
+                           const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!g_loss_rows) return fail(TCELBO_ERR_INVALID, "null upstream gradient pointer");
+    LossFusion lf; lf.on = true; lf.beta = beta; lf.g_loss = g_loss_rows; lf.g_kl = g_kl_rows;
+    return backward_impl(z, ldz, mu_all, ldmu, logvar, ldlv, b_loc, b_glob, row_offset, d, dataset_size, flags,
+                         g_log_qz, g_log_qz_prod, lf, grad_z, ldgz, grad_mu_all, ldgmu, grad_logvar, ldglv,
+                         workspace, workspace_bytes, scratch, scratch_bytes, stream);
 }
 
 #define ROWOP_CHECK(cond, msg) do { if (!(cond)) return fail(TCELBO_ERR_INVALID, msg); } while (0)

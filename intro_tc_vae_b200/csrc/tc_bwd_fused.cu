@@ -357,24 +357,39 @@ if (special) bwd_subtile<DPT, RI, JS_, PHASED, true >(tile, gq, gst, sub, lane, 
     }
 }
 
+// Elementwise over [B,D]: sum the column-split partials of the row-local sums (8 independent loads in flight), scale,
+// and add the fused KL gradient when asked (ops.py:161-163).
 __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
     const int64_t n_row = (int64_t)a.b_loc * a.d;
     const int64_t n_col = (int64_t)a.b_glob * a.d;
+    const size_t split_stride = (size_t)a.bl_pad * a.dp;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_row + n_col; idx += (int64_t)gridDim.x * blockDim.x) {
         if (idx < n_row) {
             const int i = (int)(idx / a.d), dd = (int)(idx % a.d);
             const size_t o = (size_t)i * a.dp + dd;
             float sa = 0.0f, sc = 0.0f;
-            for (int s = 0; s < a.n_js; ++s) {
-                sa += a.Apart[(size_t)s * a.bl_pad * a.dp + o];
-                sc += a.CRpart[(size_t)s * a.bl_pad * a.dp + o];
+            for (int s0 = 0; s0 < a.n_js; s0 += 8) {
+                float va[8], vc[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const bool ok = s0 + k < a.n_js;
+                    va[k] = ok ? __ldg(a.Apart + (size_t)(s0 + k) * split_stride + o) : 0.0f;
+                    vc[k] = ok ? __ldg(a.CRpart + (size_t)(s0 + k) * split_stride + o) : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { sa += va[k]; sc += vc[k]; }
             }
+            float glv = a.vr[o] * sc;
+            if (a.gk != nullptr) glv += a.gk[i] * 0.5f * (expf(a.lv[(int64_t)i * a.ldlv + dd]) - 1.0f);
             a.grad_z[(int64_t)i * a.ldgz + dd] = kTwoLn2 * a.ns[o] * sa;
-            a.grad_lv[(int64_t)i * a.ldglv + dd] = a.vr[o] * sc;
+            a.grad_lv[(int64_t)i * a.ldglv + dd] = glv;
         } else {
             const int64_t k = idx - n_row;
             const int j = (int)(k / a.d), dd = (int)(k % a.d);
-            a.grad_mu[(int64_t)j * a.ldgmu + dd] = -kTwoLn2 * a.Gpart[(size_t)j * a.dp + dd];
+            float g = -kTwoLn2 * a.Gpart[(size_t)j * a.dp + dd];
+            const int i = j - a.row_offset;
+            if (a.gk != nullptr && i >= 0 && i < a.b_loc) g += a.gk[i] * a.mu_all[(int64_t)j * a.ldmu + dd];
+            a.grad_mu[(int64_t)j * a.ldgmu + dd] = g;
         }
     }
 }

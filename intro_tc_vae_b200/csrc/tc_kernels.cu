@@ -228,26 +228,46 @@ tc_fwd_kernel(const FwdArgs a) {
     }
 }
 
-// one warp per row: sum the column-split partials, take logs, emit log_qz / log_qz_prod
+// One warp per row: sum the column-split partials (float4 per lane, 8 independent loads in flight), take logs,
+// emit log_qz / log_qz_prod and, when asked, the fused KL and (beta-1)*TC + KL of solvers/tc.py:83-89.
 __global__ void fwd_finalize_kernel(const FinArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= a.b_loc) return;
     float P = 0.0f, C = 0.0f;
-    for (int dd = lane; dd < a.dp; dd += 32) {
-        float S = 0.0f;
-        for (int s = 0; s < a.n_js; ++s) S += a.Spart[((size_t)s * a.bl_pad + row) * a.dp + dd];
-        a.S[(size_t)row * a.dp + dd] = S;
-        if (dd < a.d) {
-            const float sh = a.shift[(size_t)row * a.dp + dd];
-            P += (logf(S) + a.lw_u) + sh;
-            C += sh;
+    const size_t split_stride = (size_t)a.bl_pad * a.dp;
+    for (int d0 = 4 * lane; d0 < a.dp; d0 += 128) {
+        const float* src = a.Spart + (size_t)row * a.dp + d0;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < a.n_js; s0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                v[k] = (s0 + k < a.n_js) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(s0 + k) * split_stride))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+        }
+        *reinterpret_cast<float4*>(a.S + (size_t)row * a.dp + d0) = acc;
+        const float4 sh = *reinterpret_cast<const float4*>(a.shift + (size_t)row * a.dp + d0);
+        const float Sv[4] = {acc.x, acc.y, acc.z, acc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (d0 + e < a.d) { P += (logf(Sv[e]) + a.lw_u) + shv[e]; C += shv[e]; }
+        }
+    }
+    float kl = 0.0f;
+    if (a.lv != nullptr) {
+        for (int dd = lane; dd < a.d; dd += 32) {
+            const float l = a.lv[(int64_t)row * a.ldlv + dd], m = a.mu_loc[(int64_t)row * a.ldmu + dd];
+            kl += 1.0f + l - expf(l) - m * m;
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         P += __shfl_xor_sync(0xffffffffu, P, o);
         C += __shfl_xor_sync(0xffffffffu, C, o);
+        kl += __shfl_xor_sync(0xffffffffu, kl, o);
     }
     if (lane == 0) {
         const float2* pj = reinterpret_cast<const float2*>(a.Jpart);
@@ -259,9 +279,15 @@ __global__ void fwd_finalize_kernel(const FinArgs a) {
             m = mn;
         }
         const float J2 = m + log2f(s);
+        const float lq = kLn2 * J2 + C + a.lw_u;
         a.J2[row] = J2;
-        a.log_qz[row] = kLn2 * J2 + C + a.lw_u;
+        a.log_qz[row] = lq;
         a.log_qz_prod[row] = P;
+        if (a.lv != nullptr) {
+            kl *= -0.5f;
+            a.kl_rows[row] = kl;
+            a.loss_rows[row] = (a.beta - 1.0f) * (lq - P) + kl;
+        }
     }
 }
 
@@ -274,13 +300,33 @@ __global__ void fwd_finalize_kernel(const FinArgs a) {
 // and chunk), so accumulators never cross lanes and no shuffles are needed.
 // =====================================================================================================
 __global__ void bwd_prep_kernel(const float* __restrict__ g_log_qz, const float* __restrict__ g_log_qz_prod,
+                                const float* __restrict__ g_loss, const float* __restrict__ g_kl, float beta,
                                 const float* __restrict__ S, int b_loc, int bl_pad, int dp,
-                                float* __restrict__ gps, float* __restrict__ gj) {
+                                float* __restrict__ gps, float* __restrict__ gj, float* __restrict__ gk,
+                                float* __restrict__ zero, int64_t zero_n) {
     const int64_t n = (int64_t)bl_pad * dp;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t total = n > zero_n ? n : zero_n;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (idx < zero_n) zero[idx] = 0.0f;
+        if (idx >= n) continue;
         const int i = (int)(idx / dp);
-        gps[idx] = (i < b_loc) ? g_log_qz_prod[i] / S[idx] : 0.0f;
-        if (idx < bl_pad) gj[idx] = (idx < b_loc) ? g_log_qz[idx] : 0.0f;
+        float gP = 0.0f;
+        if (i < b_loc) {
+            if (g_log_qz_prod) gP += g_log_qz_prod[i];
+            if (g_loss) gP -= (beta - 1.0f) * g_loss[i];
+            gP /= S[idx];
+        }
+        gps[idx] = gP;
+        if (idx < bl_pad) {
+            float gJ = 0.0f, k = 0.0f;
+            if (idx < b_loc) {
+                if (g_log_qz) gJ += g_log_qz[idx];
+                if (g_loss) { gJ += (beta - 1.0f) * g_loss[idx]; k += g_loss[idx]; }
+                if (g_kl) k += g_kl[idx];
+            }
+            gj[idx] = gJ;
+            if (gk) gk[idx] = k;
+        }
     }
 }
 
@@ -674,11 +720,13 @@ cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st
     return cudaGetLastError();
 }
 
-cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g_log_qz_prod, const float* S,
-                            float* gps, float* gj, cudaStream_t st) {
+cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g_log_qz_prod, const float* g_loss, const float* g_kl,
+                            float beta, const float* S, float* gps, float* gj, float* gk, float* zero, size_t zero_n, cudaStream_t st) {
     const int64_t n = (int64_t)p.bl_pad * p.dp;
+    const int64_t total = n > (int64_t)zero_n ? n : (int64_t)zero_n;
     LaunchScope scope(kKernNone, st);
-    bwd_prep_kernel<<<grid_for(n, 256), 256, 0, st>>>(g_log_qz, g_log_qz_prod, S, p.b_loc, p.bl_pad, p.dp, gps, gj);
+    bwd_prep_kernel<<<grid_for(total, 256), 256, 0, st>>>(g_log_qz, g_log_qz_prod, g_loss, g_kl, beta, S, p.b_loc, p.bl_pad, p.dp,
+                                                           gps, gj, gk, zero, (int64_t)zero_n);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,9 @@ struct FinArgs {
     float* S; float* J2; float* log_qz; float* log_qz_prod;
     int b_loc, bl_pad, d, dp, n_js;
     float lw_u;
+    // optional fusion of solvers/tc.py:83-89: kl_i (ops.py:161-163) and loss_i = (beta-1)*(log_qz-log_qz_prod) + kl_i
+    const float* lv; int64_t ldlv; const float* mu_loc; int64_t ldmu;   // this rank's rows of logvar / mu (nullptr: no fusion)
+    float beta; float* loss_rows; float* kl_rows;
 };
 
 struct BwdRowArgs {
@@ -61,6 +64,8 @@ struct BwdFinArgs {
     const float* ns; const float* vr;
     float* grad_z; int64_t ldgz; float* grad_lv; int64_t ldglv; float* grad_mu; int64_t ldgmu;
     int b_loc, b_glob, bl_pad, bg_pad, d, dp, n_js, n_is;
+    // optional fused KL gradient (ops.py:161-163): gk_i * mu on this rank's rows of grad_mu, gk_i * 0.5*(exp(lv)-1) on grad_lv
+    const float* gk; const float* lv; int64_t ldlv; const float* mu_all; int64_t ldmu; int row_offset;
 };
 
 cudaError_t launch_col_prep(const float* mu_all, int64_t ldmu, const Plan& p, float* mu_pad, cudaStream_t st);
@@ -68,8 +73,10 @@ cudaError_t launch_row_prep(const float* z, int64_t ldz, const float* logvar, in
                             float* zs, float* ns, float* qmax, float* shift, float* vr, cudaStream_t st);
 cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st);
 cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st);
-cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g_log_qz_prod, const float* S,
-                            float* gps, float* gj, cudaStream_t st);
+// gJ_i = g_log_qz[i] + (beta-1)*g_loss[i], gP_i = g_log_qz_prod[i] - (beta-1)*g_loss[i] (either input may be null);
+// writes gps = gP/S, gj = gJ, gk = g_loss + g_kl (if gk != null) and zeroes `zero_n` floats at `zero` (the column accumulator).
+cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g_log_qz_prod, const float* g_loss, const float* g_kl,
+                            float beta, const float* S, float* gps, float* gj, float* gk, float* zero, size_t zero_n, cudaStream_t st);
 cudaError_t launch_bwd_row(const Plan& p, const BwdRowArgs& a, cudaStream_t st);
 cudaError_t launch_bwd_col(const Plan& p, const BwdColArgs& a, cudaStream_t st);
 cudaError_t launch_bwd_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st);

@@ -33,7 +33,7 @@ struct Plan {
     size_t off_scratch;                                           // forward split partials (S, J)
     size_t total_bytes;                                           // forward workspace (read-only in backward)
     // backward scratch (its own buffer, so the forward workspace stays immutable and backward can be re-run)
-    size_t boff_gps, boff_gj, boff_A, boff_CR, boff_G, bwd_bytes;
+    size_t boff_gps, boff_gj, boff_gk, boff_A, boff_CR, boff_G, bwd_bytes;
     bool save, var_col;
 };
 
@@ -116,6 +116,7 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     size_t b = 0;
     p.boff_gps = b; b = align256(b + row_arr);
     p.boff_gj = b;  b = align256(b + (size_t)p.bl_pad * sizeof(float));
+    p.boff_gk = b;  b = align256(b + (size_t)p.bl_pad * sizeof(float));
     const int n_js_max = p.n_js_bwr > p.n_js_bwf ? p.n_js_bwr : p.n_js_bwf;
     p.boff_A = b;   b = align256(b + (size_t)n_js_max * row_arr);
     p.boff_CR = b;  b = align256(b + (size_t)n_js_max * row_arr);

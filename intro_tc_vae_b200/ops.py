@@ -24,7 +24,7 @@ from . import _lib
 from .sharding import gather_rows, shard_rows
 
 __all__ = [
-    "total_correlation", "tc_terms", "kl_divergence", "kl_no_reduce", "reparameterize",
+    "total_correlation", "tc_terms", "kl_tc_loss_terms", "kl_divergence", "kl_no_reduce", "reparameterize",
     "log_importance_weight_matrix", "row_log_density",
 ]
 
@@ -134,6 +134,119 @@ def _tc_autograd_backward(ctx, g_log_qz, g_log_qz_prod, _g_ws):
 
 
 _tc_forward.register_autograd(_tc_autograd_backward, setup_context=_tc_setup_context)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused compute_kl_loss:  torch.ops.tcelbo.klloss_forward / klloss_backward
+# --------------------------------------------------------------------------------------------------
+@torch.library.custom_op("tcelbo::klloss_forward", mutates_args=(), device_types="cuda")
+def _klloss_forward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, dataset_size: int, flags: int,
+                    beta: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    lib = _lib.load()
+    z, mu_all, logvar = _rows(z), _rows(mu_all), _rows(logvar)
+    b_loc, d = z.shape
+    b_glob = mu_all.shape[0]
+    nbytes = lib.tcelbo_workspace_bytes(b_loc, b_glob, d, flags)
+    if nbytes == 0:
+        raise NotImplementedError(f"tcelbo: unsupported shape b_loc={b_loc} b_glob={b_glob} d={d} (d must be <= 512)")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+    out = torch.empty(4, b_loc, dtype=torch.float32, device=z.device)       # loss, kl, log_qz, log_qz_prod
+    with torch.cuda.device(z.device):
+        st = lib.tcelbo_klloss_forward(z.data_ptr(), z.stride(0), mu_all.data_ptr(), mu_all.stride(0),
+                                       logvar.data_ptr(), logvar.stride(0), b_loc, b_glob, row_offset, d, dataset_size,
+                                       flags, beta, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                       out[3].data_ptr(), ws.data_ptr(), nbytes, _stream(z))
+    _lib.check(st, "tcelbo_klloss_forward")
+    return out[0], out[1], out[2], out[3], ws
+
+
+@_klloss_forward.register_fake
+def _(z, mu_all, logvar, row_offset, dataset_size, flags, beta):
+    nbytes = _lib.load().tcelbo_workspace_bytes(z.shape[0], mu_all.shape[0], z.shape[1], flags)
+    b = z.shape[0]
+    return (z.new_empty(b), z.new_empty(b), z.new_empty(b), z.new_empty(b), z.new_empty(nbytes, dtype=torch.uint8))
+
+
+@torch.library.custom_op("tcelbo::klloss_backward", mutates_args=(), device_types="cuda")
+def _klloss_backward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, dataset_size: int, flags: int, beta: float,
+                     g_loss: Tensor, g_kl: Optional[Tensor], g_log_qz: Optional[Tensor], g_log_qz_prod: Optional[Tensor],
+                     workspace: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    lib = _lib.load()
+    z, mu_all, logvar = _rows(z), _rows(mu_all), _rows(logvar)
+    b_loc, d = z.shape
+    b_glob = mu_all.shape[0]
+    g_loss = g_loss.contiguous()
+    opt = [t.contiguous() if t is not None else None for t in (g_kl, g_log_qz, g_log_qz_prod)]
+    grad_z = torch.empty(b_loc, d, dtype=torch.float32, device=z.device)
+    grad_mu = torch.empty(b_glob, d, dtype=torch.float32, device=z.device)
+    grad_lv = torch.empty(b_loc, d, dtype=torch.float32, device=z.device)
+    nscratch = lib.tcelbo_backward_scratch_bytes(b_loc, b_glob, d, flags)
+    scratch = torch.empty(nscratch, dtype=torch.uint8, device=z.device)
+    with torch.cuda.device(z.device):
+        st = lib.tcelbo_klloss_backward(z.data_ptr(), z.stride(0), mu_all.data_ptr(), mu_all.stride(0),
+                                        logvar.data_ptr(), logvar.stride(0), b_loc, b_glob, row_offset, d, dataset_size,
+                                        flags, beta, g_loss.data_ptr(), *(t.data_ptr() if t is not None else None for t in opt),
+                                        grad_z.data_ptr(), d, grad_mu.data_ptr(), d, grad_lv.data_ptr(), d,
+                                        workspace.data_ptr(), workspace.numel(), scratch.data_ptr(), nscratch, _stream(z))
+    _lib.check(st, "tcelbo_klloss_backward")
+    return grad_z, grad_mu, grad_lv
+
+
+@_klloss_backward.register_fake
+def _(z, mu_all, logvar, row_offset, dataset_size, flags, beta, g_loss, g_kl, g_log_qz, g_log_qz_prod, workspace):
+    return (z.new_empty(z.shape), mu_all.new_empty(mu_all.shape), logvar.new_empty(logvar.shape))
+
+
+def _klloss_setup_context(ctx, inputs, output):
+    z, mu_all, logvar, row_offset, dataset_size, flags, beta = inputs
+    ctx.save_for_backward(z, mu_all, logvar, output[4])
+    ctx.meta = (row_offset, dataset_size, flags, beta)
+
+
+def _klloss_autograd_backward(ctx, g_loss, g_kl, g_log_qz, g_log_qz_prod, _g_ws):
+    z, mu_all, logvar, ws = ctx.saved_tensors
+    row_offset, dataset_size, flags, beta = ctx.meta
+    if not flags & _lib.SAVE_FOR_BACKWARD:
+        raise RuntimeError("tcelbo: forward ran without TCELBO_SAVE_FOR_BACKWARD but a gradient was requested")
+    if g_loss is None:
+        g_loss = torch.zeros(z.shape[0], dtype=torch.float32, device=z.device)
+    gz, gmu, glv = _klloss_backward(z, mu_all, logvar, row_offset, dataset_size, flags, beta,
+                                    g_loss, g_kl, g_log_qz, g_log_qz_prod, ws)
+    return gz, gmu, glv, None, None, None, None
+
+
+_klloss_forward.register_autograd(_klloss_autograd_backward, setup_context=_klloss_setup_context)
+
+
+def kl_tc_loss_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, beta: float, estimator: str = "mss",
+                     group=None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """One fused evaluation of ``TCSovler._compute_kl_loss_simple`` (solvers/tc.py:69-89) per sample:
+
+        loss_i = (beta - 1) * (log_qz_i - log_qz_prod_i) + kl_i ,   kl_i = ops.py:161-163
+
+    Returns ``(loss [B], kl [B], log_qz [B], log_qz_prod [B])``.  KL and the combine are folded into the TC
+    kernels' finalize steps (forward and backward), so no separate KL or elementwise kernels are launched.
+    ``group`` row-shards the batch exactly as in :func:`tc_terms`.
+    """
+    for name, t in (("z", z), ("mu", mu), ("logvar", logvar)):
+        _check(name, t)
+    if not (z.shape == mu.shape == logvar.shape):
+        raise ValueError(f"z, mu, logvar must have one shape, got {tuple(z.shape)}, {tuple(mu.shape)}, {tuple(logvar.shape)}")
+    if estimator not in ("mss", "mws"):
+        raise ValueError(f"estimator must be 'mss' or 'mws', got {estimator!r}")
+    flags = (_lib.EST_MSS if estimator == "mss" else _lib.EST_MWS) | _lib.VAR_ROW
+    if torch.is_grad_enabled() and (z.requires_grad or mu.requires_grad or logvar.requires_grad):
+        flags |= _lib.SAVE_FOR_BACKWARD
+    row_offset, mu_all = 0, mu
+    if group is not None:
+        import torch.distributed as dist
+        if dist.get_world_size(group) > 1:
+            row_offset, _ = shard_rows(group, z.shape[0])
+            mu_all = gather_rows(mu, group)
+    if estimator == "mss" and mu_all.shape[0] == 1:
+        raise ZeroDivisionError("float division by zero")       # ops.py:44 with M = B-1 = 0
+    loss, kl, log_qz, log_qz_prod, _ = _klloss_forward(z, mu_all, logvar, row_offset, int(dataset_size), flags, float(beta))
+    return loss, kl, log_qz, log_qz_prod
 
 
 def tc_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, estimator: str = "mss",

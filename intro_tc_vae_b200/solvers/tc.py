@@ -30,11 +30,16 @@ class TCLossMixin:
         if beta is None:
             beta = self.beta_kl
         dataset_size = len(self.dataset)
-        kl_loss = ops.kl_divergence(logvar, mu, reduce=reduce)
-        tc = ops.total_correlation(z, mu, logvar, dataset_size, reduce=reduce, group=getattr(self, "process_group", None))
-        if write:
-            self.write_scalar(SingletonWriter().cur_iter, "kl_loss_unscaled", kl_loss)   # KL only, as in the reference
-        return (beta - 1.0) * tc + kl_loss
+        # one fused op: per-sample (beta-1)*tc_i + kl_i and kl_i (KL and the combine ride in the TC kernels' epilogues)
+        loss, kl, _, _ = ops.kl_tc_loss_terms(z, mu, logvar, dataset_size, beta, "mss", getattr(self, "process_group", None))
+        if write:                                                    # KL only, as in the reference (solvers/tc.py:87-88)
+            kl_loss = kl.sum() if reduce == "sum" else (kl.mean() if reduce == "mean" else kl)
+            self.write_scalar(SingletonWriter().cur_iter, "kl_loss_unscaled", kl_loss)
+        if reduce == "mean":                                         # mean((b-1)*tc + kl) == (b-1)*mean(tc) + mean(kl)
+            return loss.mean()
+        if reduce == "sum":                                          # kl summed, tc per sample (ops.py:86-89 treats "sum" as none)
+            return (loss - kl) + kl.sum()
+        return loss
 
     def _compute_kl_loss_full(self, z: Optional[Tensor], mu: Tensor, logvar: Tensor, reduce: str = "mean",
                               beta: float = None, write: bool = False) -> Tensor:

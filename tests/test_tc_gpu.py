@@ -358,6 +358,10 @@ def test_solver_mixin_simple_path(golden, name):
     ref = float(golden[pre + "simple_mean"])
     scale = max(1.0, beta * np.abs(golden[pre + "log_qz_prod"]).mean() / abs(ref))
     assert loss.dim() == 0 and abs(loss.item() - ref) < LOSS_RTOL * abs(ref) * scale
+    loss.backward(retain_graph=True)                            # fused KL + TC backward, through z = mu + eps*std
+    assert relerr(mu.grad, golden[pre + "simple_mean_dmu"]) < GRAD_RTOL
+    assert relerr(lv.grad, golden[pre + "simple_mean_dlv"]) < GRAD_RTOL
+    mu.grad = lv.grad = None
     assert solver.written[0][0] == "kl_loss_unscaled"
     assert abs(solver.written[0][1] - float(golden[pre + "kl"].mean())) < LOSS_RTOL * abs(float(golden[pre + "kl"].mean()))
     per = TCLossMixin.compute_kl_loss(solver, z, mu, lv, reduce="none", beta=float(beta))
@@ -390,3 +394,30 @@ def test_column_variance_seeded_against_cpu_oracle(B, D):
     assert abs(loss.item() - loss_o.item()) < LOSS_RTOL * beta * prod.abs().mean().item()
     assert relerr(mu.grad, mu_o.grad) < GRAD_RTOL
     assert relerr(lv.grad, lv_o.grad) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("B,D,family", [(256, 128, "base"), (320, 64, "sharp"), (1000, 128, "sharp")])
+def test_fused_loss_equals_composition(B, D, family):
+    """kl_tc_loss_terms == (beta-1)*total_correlation + kl_divergence, values and all gradients, incl. the extra outputs."""
+    ops = _ops()
+    N, beta = 16704, 3.5
+    mu_c, lv_c, eps_c = _random_latents(B, D, family, seed=31)
+    w1 = torch.linspace(0.2, 1.7, B, device="cuda:0")
+    w2 = torch.linspace(-0.5, 0.5, B, device="cuda:0")
+    outs = []
+    for fused in (False, True):
+        mu = mu_c.cuda().requires_grad_(True)
+        lv = lv_c.cuda().requires_grad_(True)
+        z = ops.reparameterize(mu, lv, eps_c.cuda())
+        if fused:
+            loss, kl, lq, lqp = ops.kl_tc_loss_terms(z, mu, lv, N, beta)
+        else:
+            lqp, lq = ops.tc_terms(z, mu, lv, N)
+            kl = ops.kl_divergence(lv, mu, reduce="none")
+            loss = (beta - 1.0) * (lq - lqp) + kl
+        ((loss * w1).sum() + (kl * w2).sum() + 0.3 * (lq * w2).sum() - 0.2 * (lqp * w1).sum()).backward()
+        outs.append((loss.detach(), kl.detach(), mu.grad, lv.grad))
+    assert relerr(outs[1][0], outs[0][0]) < 2e-6
+    assert relerr(outs[1][1], outs[0][1]) < 2e-6
+    assert relerr(outs[1][2], outs[0][2]) < 1e-5
+    assert relerr(outs[1][3], outs[0][3]) < 1e-5
