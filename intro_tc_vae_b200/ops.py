@@ -150,7 +150,7 @@ def _klloss_forward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, 
     if nbytes == 0:
         raise NotImplementedError(f"tcelbo: unsupported shape b_loc={b_loc} b_glob={b_glob} d={d} (d must be <= 512)")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
-    out = torch.empty(4, b_loc, dtype=torch.float32, device=z.device)       # loss, kl, log_qz, log_qz_prod
+    out = [torch.empty(b_loc, dtype=torch.float32, device=z.device) for _ in range(4)]   # loss, kl, log_qz, log_qz_prod
     with torch.cuda.device(z.device):
         st = lib.tcelbo_klloss_forward(z.data_ptr(), z.stride(0), mu_all.data_ptr(), mu_all.stride(0),
                                        logvar.data_ptr(), logvar.stride(0), b_loc, b_glob, row_offset, d, dataset_size,
