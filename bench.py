@@ -396,9 +396,15 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "wall_s_timed_region": t_wall1 - t_wall0,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down of an NCCL communicator that was used inside a captured CUDA graph can block; the numbers are
+        # already printed, so synchronise the ranks and leave without running destructors.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
