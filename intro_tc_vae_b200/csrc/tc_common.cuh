@@ -69,18 +69,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
                  :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a lost transaction traps (-> CUDA error) after ~2 s instead of hanging the GPU.
+// Wait for the phase with the given parity.  Fast path: one try_wait.  Slow path: try_wait with a suspend-time
+// hint, so the hardware parks the warp until the phase completes (or ~20 us pass) instead of spinning through
+// issue slots the other warps need.  Bounded: a lost transaction traps (-> CUDA error) after ~2^17 hinted waits
+// (seconds) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    long long t0 = 0;
-    for (;;) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) break;
-        const long long now = clock64();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 4000000000LL) __trap();
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    for (int spin = 0; ; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+        if (done) return;
+        if (spin > (1 << 17)) __trap();
     }
 }
 // global -> shared bulk copy, completion signalled on `bar` (bytes % 16 == 0, both addresses 16B aligned)
