@@ -185,7 +185,7 @@ __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, cons
     }
 }
 
-template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED>
+template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF>
 __global__ void __launch_bounds__(NW * 32, MINB)
 tc_bwd_fused_kernel(const BwdFusedArgs a) {
     using GEO = BwdGeom<DPT, JS_>;
@@ -200,11 +200,11 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
     float* mu_tiles = reinterpret_cast<float*>(smem_raw);                    // [kStages][TILE]
     float* s2_tiles = mu_tiles + (size_t)kStages * TILE;                     // [kStages][ROWS][JT]
     float* gq_buf = s2_tiles + (size_t)kStages * ROWS * JT;                  // [NW][RI][JT]
-    float* gstage = gq_buf + (size_t)NW * RI * JT;                           // [2][NW][JS][DP]
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gstage + 2 * (size_t)GST);
+    float* gstage = gq_buf + (size_t)NW * RI * JT;                           // [NBUF][NW][JS][DP]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gstage + NBUF * (size_t)GST);
     uint64_t* bar_empty = bar_full + kStages;
-    uint64_t* g_full = bar_empty + kStages;                                  // [2] staging buffer written by all warps
-    uint64_t* g_empty = g_full + 2;                                          // [2] staging buffer reduced by all warps
+    uint64_t* g_full = bar_empty + kStages;                                  // [NBUF] staging buffer written by all warps
+    uint64_t* g_empty = g_full + NBUF;                                       // [NBUF] staging buffer reduced by all warps
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * ROWS + warp * RI;
@@ -253,7 +253,7 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NW); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&g_full[s], NW); mbar_init(&g_empty[s], NW); }
+        for (int s = 0; s < NBUF; ++s) { mbar_init(&g_full[s], NW); mbar_init(&g_empty[s], NW); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -273,9 +273,10 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
     if (warp == 0 && ntiles > 0) issue(0);
 
     // reduce this thread's share of staging buffer (k & 1) (sub-tile k, columns starting at col0) into Gacc
+    // With NBUF >= 3 a warp may run a whole sub-tile ahead of the slowest warp of its CTA before it blocks here.
     auto reduce_share = [&](int k, int col0) {
-        const int b = k & 1;
-        mbar_wait(&g_full[b], (k >> 1) & 1);
+        const int b = k % NBUF;
+        mbar_wait(&g_full[b], (k / NBUF) & 1);
         const float* gsb = gstage + (size_t)b * GST;
         for (int f = threadIdx.x; f < JS * DP / 4; f += NW * 32) {
             const int col = f / (DP / 4), chunk = f % (DP / 4);
@@ -317,8 +318,8 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
         __syncwarp();
 
         for (int sub = 0; sub < JT; sub += JS, ++k) {
-            const int b = k & 1;
-            if (k >= 2) mbar_wait(&g_empty[b], ((k >> 1) - 1) & 1);           // everyone finished reducing sub-tile k-2
+            const int b = k % NBUF;
+            if (k >= NBUF) mbar_wait(&g_empty[b], ((k / NBUF) - 1) & 1);      // everyone finished reducing sub-tile k-NBUF
             float* gst = gstage + (size_t)b * GST + (size_t)warp * JS * DP;
 if (special) bwd_subtile<DPT, RI, JS_, PHASED, true >(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
             else         bwd_subtile<DPT, RI, JS_, PHASED, false>(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
@@ -400,15 +401,15 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
 static int g_bwd_variant = -1;      // -1: default per shape; set through tcelbo_set_tuning("bwd_variant", v)
 void set_bwd_variant(int v) { g_bwd_variant = v; }
 
-template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED>
+template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF = 2>
 static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, int* n_js_out, cudaStream_t st) {
     using GEO = BwdGeom<DPT, JS_>;
     constexpr int ROWS = NW * RI;
     const size_t smem = ((size_t)kStages * GEO::JT * GEO::DP + (size_t)kStages * ROWS * GEO::JT + (size_t)NW * RI * GEO::JT
-                         + 2 * (size_t)NW * GEO::JS * GEO::DP) * sizeof(float) + (2 * kStages + 4) * sizeof(uint64_t);
+                         + NBUF * (size_t)NW * GEO::JS * GEO::DP) * sizeof(float) + (2 * kStages + 2 * NBUF) * sizeof(uint64_t);
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
-        auto kern = tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED>;
+        auto kern = tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 0;
@@ -422,7 +423,7 @@ static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, int* n_js_o
     a.js_len = js_len;
     *n_js_out = n_js;
     LaunchScope scope(kKernBwdRow, st);
-    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED><<<dim3(n_rb, n_js), NW * 32, smem, st>>>(a);
+    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF><<<dim3(n_rb, n_js), NW * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -442,6 +443,12 @@ cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out
                 case 8:  return launch_bwd_fused_t<4, 2, 12, 2, 4, true >(p, a, n_js_out, st);
                 case 9:  return launch_bwd_fused_t<4, 4, 16, 1, 8, true >(p, a, n_js_out, st);
                 case 10: return launch_bwd_fused_t<4, 2, 16, 2, 4, true >(p, a, n_js_out, st);
+                case 11: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 3>(p, a, n_js_out, st);   // three staging buffers
+                case 12: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 4>(p, a, n_js_out, st);
+                case 13: return launch_bwd_fused_t<4, 4, 8, 2, 4, false, 3>(p, a, n_js_out, st);
+                case 14: return launch_bwd_fused_t<4, 3, 8, 2, 2, false, 4>(p, a, n_js_out, st);
+                case 15: return launch_bwd_fused_t<4, 4, 12, 1, 8, false, 3>(p, a, n_js_out, st);
+                case 16: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 2>(p, a, n_js_out, st);
                 case 0:  return launch_bwd_fused_t<4, 4, 12, 1, 8, false>(p, a, n_js_out, st);
                 default: return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);   // best of the sweep in profiles/
             }
