@@ -49,7 +49,7 @@ template <int DPT, int JS_> struct BwdGeom {
 };
 
 // One (row, column) pair of this lane's DPT dims, packed two dims per instruction.
-template <int NP, bool kWeighted>
+template <int NP, bool kWeighted, int ABL = 0>
 __device__ __forceinline__ void bwd_pairs(const u64 (&mu2)[NP], const u64 (&zs2)[NP], const u64 (&ns2)[NP],
                                           const float (&qmx)[2 * NP], const u64 (&gps2)[NP], float gq, float rho,
                                           u64 (&A2)[NP], u64 (&CR2)[NP], u64 (&G2)[NP]) {
@@ -64,7 +64,7 @@ __device__ __forceinline__ void bwd_pairs(const u64 (&mu2)[NP], const u64 (&zs2)
         float q0, q1;
         unpack2(q2, q0, q1);
         const float c0 = fmin_nan(q0, qmx[2 * p]), c1 = fmin_nan(q1, qmx[2 * p + 1]);
-        u64 e2 = pack2(ex2(-c0), ex2(-c1));
+        u64 e2 = (ABL == 2) ? pack2(1.0f - c0, 1.0f - c1) : pack2(ex2(-c0), ex2(-c1));     // ABL 2: no MUFU (timing ablation only)
         if (kWeighted) e2 = fmul2(e2, rho2);
         const u64 coef2 = ffma2(e2, gps2[p], gq2);
         const u64 m2 = pack2(fset_le(q0, qmx[2 * p]), fset_le(q1, qmx[2 * p + 1]));
@@ -75,6 +75,28 @@ __device__ __forceinline__ void bwd_pairs(const u64 (&mu2)[NP], const u64 (&zs2)
         CR2[p] = ffma2(r2, u2, CR2[p]);
         G2[p] = ffma2(t2, ns2[p], G2[p]);
     }
+}
+
+// Scalar, predicated form of the same arithmetic.  On B200 a packed FFMA2 with three distinct register pairs costs
+// ~3.1 dispatch cycles and the mask needs an extra FMUL2, whereas scalar 3-operand FFMAs cost ~1.25 and the clamp mask
+// can ride on a predicate (tools/rf_probe.cu, profiles/r1_bwd_variant_sweep.md): ~12 instead of ~14.2 cycles per element.
+template <bool kWeighted>
+__device__ __forceinline__ void bwd_elem_pred(float mu, float zs, float ns, float qmx, float gps, float gq, float rho,
+                                              float& A, float& CR, float& G) {
+    const float dl = fmaf(mu, ns, zs);
+    const float q = dl * dl;
+    const float c = fmin_nan(q, qmx);
+    float e = ex2(-c);
+    if (kWeighted) e *= rho;
+    const float coef = fmaf(e, gps, gq);
+    const float t = coef * dl;
+    const float u = fmaf(c, kTwoLn2, -1.0f);
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.leu.f32 p, %3, %4;\n\t"                 // unmasked (or NaN: propagate)
+        "@p add.f32 %0, %0, %5;\n\t"
+        "@p fma.rn.f32 %1, %6, %7, %1;\n\t"
+        "@p fma.rn.f32 %2, %5, %8, %2;\n\t}"
+        : "+f"(A), "+f"(CR), "+f"(G) : "f"(q), "f"(qmx), "f"(t), "f"(coef), "f"(u), "f"(ns));
 }
 
 // Same arithmetic for a group of RG rows in two phases: every MUFU of the group is issued before any
@@ -121,7 +143,7 @@ __device__ __forceinline__ void bwd_rows_phased(const u64 (&mu2)[NP], const u64 
 
 // All JS columns of one staging sub-tile for this warp's RI rows.  Templated on the special-tile case so
 // the GV unrolled columns form ONE basic block and independent (row, column) chains can be interleaved.
-template <int DPT, int RI, int JS_, bool PHASED, bool kSpecial>
+template <int DPT, int RI, int JS_, bool PHASED, bool kSpecial, int ABL = 0, bool SCALAR = false>
 __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, const float* __restrict__ gq, float* __restrict__ gst,
                                             int sub, int lane, int jt0, int i_glob0, const Weights& w,
                                             const u64 (&zs2)[RI][BwdGeom<DPT, JS_>::NP], const u64 (&ns2)[RI][BwdGeom<DPT, JS_>::NP],
@@ -134,7 +156,10 @@ __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, cons
     for (int g0 = 0; g0 < JS; g0 += GV) {
         float gqv[RI][GV];
 #pragma unroll
-        for (int r = 0; r < RI; ++r) VecLd<GV>::ld(gq + r * JT + sub + g0, gqv[r]);
+        for (int r = 0; r < RI; ++r) {
+            if (ABL == 3) { for (int u = 0; u < GV; ++u) gqv[r][u] = 1e-3f * (float)(r + 1); }      // ABL 3: no joint-coefficient loads
+            else VecLd<GV>::ld(gq + r * JT + sub + g0, gqv[r]);
+        }
 #pragma unroll
         for (int u = 0; u < GV; ++u) {
             const int jj = sub + g0 + u;
@@ -157,7 +182,20 @@ __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, cons
                 rho[r] = 1.0f;
                 if (kSpecial) { float l2; weight_of(w, i_glob0 + r, jt0 + jj, rho[r], l2); }
             }
-            if (PHASED) {
+            if (SCALAR) {
+#pragma unroll
+                for (int r = 0; r < RI; ++r) {
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        float m0, m1, z0, z1, n0, n1, g0_, g1_, a0, a1, c0, c1, G0, G1;
+                        unpack2(mu2[p], m0, m1); unpack2(zs2[r][p], z0, z1); unpack2(ns2[r][p], n0, n1);
+                        unpack2(gps2[r][p], g0_, g1_); unpack2(A2[r][p], a0, a1); unpack2(CR2[r][p], c0, c1); unpack2(G2[p], G0, G1);
+                        bwd_elem_pred<kSpecial>(m0, z0, n0, qmx[r][2 * p], g0_, gqv[r][u], rho[r], a0, c0, G0);
+                        bwd_elem_pred<kSpecial>(m1, z1, n1, qmx[r][2 * p + 1], g1_, gqv[r][u], rho[r], a1, c1, G1);
+                        A2[r][p] = pack2(a0, a1); CR2[r][p] = pack2(c0, c1); G2[p] = pack2(G0, G1);
+                    }
+                }
+            } else if (PHASED) {
 #pragma unroll
                 for (int rg = 0; rg < RI; rg += RG)
                     bwd_rows_phased<NP, RG, kSpecial>(mu2, &zs2[rg], &ns2[rg], &qmx[rg], &gps2[rg], &gqv[rg][u], GV, &rho[rg],
@@ -165,7 +203,12 @@ __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, cons
             } else {
 #pragma unroll
                 for (int r = 0; r < RI; ++r)
-                    bwd_pairs<NP, kSpecial>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], rho[r], A2[r], CR2[r], G2);
+                    bwd_pairs<NP, kSpecial, ABL>(mu2, zs2[r], ns2[r], qmx[r], gps2[r], gqv[r][u], rho[r], A2[r], CR2[r], G2);
+            }
+            if (ABL == 1) {                                        // ABL 1: fold G into A, no staging (timing ablation only)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) A2[0][p] = fadd2(A2[0][p], G2[p]);
+                continue;
             }
             // warp-partial column gradient -> staging buffer [warp][column][dim]
             float vg[DPT];
@@ -185,7 +228,7 @@ __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, cons
     }
 }
 
-template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF>
+template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF, int ABL, bool SCALAR>
 __global__ void __launch_bounds__(NW * 32, MINB)
 tc_bwd_fused_kernel(const BwdFusedArgs a) {
     using GEO = BwdGeom<DPT, JS_>;
@@ -319,10 +362,11 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
 
         for (int sub = 0; sub < JT; sub += JS, ++k) {
             const int b = k % NBUF;
-            if (k >= NBUF) mbar_wait(&g_empty[b], ((k / NBUF) - 1) & 1);      // everyone finished reducing sub-tile k-NBUF
+            if (ABL != 1 && k >= NBUF) mbar_wait(&g_empty[b], ((k / NBUF) - 1) & 1);   // everyone finished reducing sub-tile k-NBUF
             float* gst = gstage + (size_t)b * GST + (size_t)warp * JS * DP;
-if (special) bwd_subtile<DPT, RI, JS_, PHASED, true >(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
-            else         bwd_subtile<DPT, RI, JS_, PHASED, false>(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
+            if (special) bwd_subtile<DPT, RI, JS_, PHASED, true, ABL, SCALAR>(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
+            else         bwd_subtile<DPT, RI, JS_, PHASED, false, ABL, SCALAR>(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
+            if (ABL == 1) continue;                                  // timing ablation: no staging hand-off / reduction
             __syncwarp();
             if (lane == 0) mbar_arrive(&g_full[b]);
             if (k >= 1) reduce_share(k - 1, prev_col0);                      // the other buffer: its writers are long done
@@ -331,7 +375,7 @@ if (special) bwd_subtile<DPT, RI, JS_, PHASED, true >(tile, gq, gst, sub, lane, 
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[st]);
     }
-    if (k >= 1) reduce_share(k - 1, prev_col0);
+    if (ABL != 1 && k >= 1) reduce_share(k - 1, prev_col0);
 
     // ---- row-local partial sums of this (row block, column split)
 #pragma unroll
@@ -401,7 +445,7 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
 static int g_bwd_variant = -1;      // -1: default per shape; set through tcelbo_set_tuning("bwd_variant", v)
 void set_bwd_variant(int v) { g_bwd_variant = v; }
 
-template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF = 2>
+template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF = 2, int ABL = 0, bool SCALAR = false>
 static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, int* n_js_out, cudaStream_t st) {
     using GEO = BwdGeom<DPT, JS_>;
     constexpr int ROWS = NW * RI;
@@ -409,7 +453,7 @@ static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, int* n_js_o
                          + NBUF * (size_t)NW * GEO::JS * GEO::DP) * sizeof(float) + (2 * kStages + 2 * NBUF) * sizeof(uint64_t);
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
-        auto kern = tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF>;
+        auto kern = tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 0;
@@ -423,7 +467,7 @@ static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, int* n_js_o
     a.js_len = js_len;
     *n_js_out = n_js;
     LaunchScope scope(kKernBwdRow, st);
-    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF><<<dim3(n_rb, n_js), NW * 32, smem, st>>>(a);
+    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR><<<dim3(n_rb, n_js), NW * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -449,6 +493,13 @@ cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out
                 case 14: return launch_bwd_fused_t<4, 3, 8, 2, 2, false, 4>(p, a, n_js_out, st);
                 case 15: return launch_bwd_fused_t<4, 4, 12, 1, 8, false, 3>(p, a, n_js_out, st);
                 case 16: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 2>(p, a, n_js_out, st);
+                case 30: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, true>(p, a, n_js_out, st);   // scalar predicated loop
+                case 31: return launch_bwd_fused_t<4, 4, 8, 2, 8, false, 2, 0, true>(p, a, n_js_out, st);
+                case 32: return launch_bwd_fused_t<4, 4, 12, 1, 8, false, 2, 0, true>(p, a, n_js_out, st);
+                case 33: return launch_bwd_fused_t<4, 2, 8, 3, 4, false, 2, 0, true>(p, a, n_js_out, st);
+                case 20: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 1>(p, a, n_js_out, st);   // ablations (wrong results, timing only)
+                case 21: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 2>(p, a, n_js_out, st);
+                case 22: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 3>(p, a, n_js_out, st);
                 case 0:  return launch_bwd_fused_t<4, 4, 12, 1, 8, false>(p, a, n_js_out, st);
                 default: return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);   // best of the sweep in profiles/
             }
