@@ -214,9 +214,7 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
     float* CRpart = at<float>(scratch, p.boff_CR);
     float* Gpart = at<float>(scratch, p.boff_G);
 
-    static const bool two_pass = (std::getenv("TCELBO_BWD_TWOPASS") != nullptr);   // A/B switch: older two-sweep backward
-    const bool use_fused = p.var_col || !two_pass;
-    const size_t zero_n = use_fused ? (size_t)(p.var_col ? 2 : 1) * p.bg_pad * p.dp : 0;
+    const size_t zero_n = (size_t)(p.var_col ? 2 : 1) * p.bg_pad * p.dp;
     if ((e = launch_bwd_prep(p, g_log_qz, g_log_qz_prod, lf.g_loss, lf.g_kl, lf.beta, S, gps, gj, lf.on ? gk : nullptr,
                              Gpart, zero_n, st)) != cudaSuccess) return fail_cuda(e, "bwd_prep");
 
@@ -239,26 +237,9 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
         if ((e = launch_bwd_colvar_finalize(p, fa, mu_pad, Glv, st)) != cudaSuccess) return fail_cuda(e, "bwd_colvar_finalize");
         return TCELBO_OK;
     }
-    if (use_fused) {
-        // single fused sweep: row-local sums in registers, column sums via smem staging + red.global
-        if ((e = launch_bwd_fused(p, ua, &fa.n_js, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");
-        if ((e = launch_bwd_fused_finalize(p, fa, st)) != cudaSuccess) return fail_cuda(e, "bwd_fused_finalize");
-        return TCELBO_OK;
-    }
-    if (lf.on) return fail(TCELBO_ERR_INVALID, "TCELBO_BWD_TWOPASS does not support the fused loss entry points");
-
-    BwdRowArgs ra;
-    ra.zs = zs; ra.ns = ns; ra.qmax = qmax; ra.gps = gps; ra.gj = gj; ra.J2 = J2; ra.mu_pad = mu_pad;
-    ra.s2 = s2; ra.ld_s2 = p.ld_s2; ra.Apart = Apart; ra.CRpart = CRpart;
-    ra.b_loc = b_loc; ra.bl_pad = p.bl_pad; ra.bg_pad = p.bg_pad; ra.row_offset = row_offset; ra.js_len = p.js_len_bwr; ra.w = w;
-    if ((e = launch_bwd_row(p, ra, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_row");
-    BwdColArgs ca;
-    ca.zs = zs; ca.ns = ns; ca.qmax = qmax; ca.gps = gps; ca.gj = gj; ca.J2 = J2; ca.mu_pad = mu_pad;
-    ca.s2 = s2; ca.ld_s2 = p.ld_s2; ca.Gpart = Gpart;
-    ca.b_loc = b_loc; ca.bl_pad = p.bl_pad; ca.bg_pad = p.bg_pad; ca.row_offset = row_offset; ca.is_len = p.is_len; ca.w = w;
-    if ((e = launch_bwd_col(p, ca, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_col");
-    fa.n_js = p.n_js_bwr; fa.n_is = p.n_is;
-    if ((e = launch_bwd_finalize(p, fa, st)) != cudaSuccess) return fail_cuda(e, "bwd_finalize");
+    // single fused sweep: row-local sums in registers, column sums via smem staging + red.global
+    if ((e = launch_bwd_fused(p, ua, &fa.n_js, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");
+    if ((e = launch_bwd_fused_finalize(p, fa, st)) != cudaSuccess) return fail_cuda(e, "bwd_fused_finalize");
     return TCELBO_OK;
 }
 

@@ -476,32 +476,17 @@ cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out
         case 1:  return launch_bwd_fused_t<1, 4, 12, 1, 8, false>(p, a, n_js_out, st);
         case 2:  return launch_bwd_fused_t<2, 4, 12, 1, 8, false>(p, a, n_js_out, st);
         case 4:
-            switch (g_bwd_variant) {                 // tuning matrix for the headline shape (D = 128)
-                case 1:  return launch_bwd_fused_t<4, 4, 12, 1, 8, true >(p, a, n_js_out, st);
-                case 2:  return launch_bwd_fused_t<4, 4, 8, 2, 8, false>(p, a, n_js_out, st);
-                case 3:  return launch_bwd_fused_t<4, 4, 8, 2, 8, true >(p, a, n_js_out, st);
-                case 4:  return launch_bwd_fused_t<4, 2, 8, 3, 4, false>(p, a, n_js_out, st);
-                case 5:  return launch_bwd_fused_t<4, 2, 8, 3, 4, true >(p, a, n_js_out, st);
-                case 6:  return launch_bwd_fused_t<4, 2, 16, 1, 8, true >(p, a, n_js_out, st);
-                case 7:  return launch_bwd_fused_t<4, 3, 8, 2, 8, true >(p, a, n_js_out, st);
-                case 8:  return launch_bwd_fused_t<4, 2, 12, 2, 4, true >(p, a, n_js_out, st);
-                case 9:  return launch_bwd_fused_t<4, 4, 16, 1, 8, true >(p, a, n_js_out, st);
-                case 10: return launch_bwd_fused_t<4, 2, 16, 2, 4, true >(p, a, n_js_out, st);
-                case 11: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 3>(p, a, n_js_out, st);   // three staging buffers
-                case 12: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 4>(p, a, n_js_out, st);
-                case 13: return launch_bwd_fused_t<4, 4, 8, 2, 4, false, 3>(p, a, n_js_out, st);
-                case 14: return launch_bwd_fused_t<4, 3, 8, 2, 2, false, 4>(p, a, n_js_out, st);
-                case 15: return launch_bwd_fused_t<4, 4, 12, 1, 8, false, 3>(p, a, n_js_out, st);
-                case 16: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 2>(p, a, n_js_out, st);
-                case 30: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, true>(p, a, n_js_out, st);   // scalar predicated loop
-                case 31: return launch_bwd_fused_t<4, 4, 8, 2, 8, false, 2, 0, true>(p, a, n_js_out, st);
-                case 32: return launch_bwd_fused_t<4, 4, 12, 1, 8, false, 2, 0, true>(p, a, n_js_out, st);
-                case 33: return launch_bwd_fused_t<4, 2, 8, 3, 4, false, 2, 0, true>(p, a, n_js_out, st);
-                case 20: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 1>(p, a, n_js_out, st);   // ablations (wrong results, timing only)
-                case 21: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 2>(p, a, n_js_out, st);
-                case 22: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 3>(p, a, n_js_out, st);
-                case 0:  return launch_bwd_fused_t<4, 4, 12, 1, 8, false>(p, a, n_js_out, st);
-                default: return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);   // best of the sweep in profiles/
+            switch (g_bwd_variant) {                 // tuning matrix for the headline shape (D = 128); see profiles/r1_bwd_variant_sweep.md
+                case 0:  return launch_bwd_fused_t<4, 4, 12, 1, 8, false>(p, a, n_js_out, st);            // 12 warps x 168 regs, 1 CTA/SM
+                case 1:  return launch_bwd_fused_t<4, 4, 12, 1, 8, true >(p, a, n_js_out, st);            //   + two-phase loop body
+                case 2:  return launch_bwd_fused_t<4, 4, 8, 2, 8, false>(p, a, n_js_out, st);             // 4 rows/warp, 2 CTAs/SM (spills)
+                case 4:  return launch_bwd_fused_t<4, 2, 8, 3, 4, false>(p, a, n_js_out, st);             // 2 rows/warp, 3 CTAs/SM
+                case 11: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 3>(p, a, n_js_out, st);          // three staging buffers
+                case 30: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, true>(p, a, n_js_out, st); // scalar predicated loop
+                case 20: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 1>(p, a, n_js_out, st);       // ablation: no column-gradient path
+                case 21: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 2>(p, a, n_js_out, st);       // ablation: no MUFU
+                case 22: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 3>(p, a, n_js_out, st);       // ablation: no joint-coefficient loads
+                default: return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);             // best of the sweep
             }
         case 8:  return launch_bwd_fused_t<8, 2, 12, 1, 4, false>(p, a, n_js_out, st);
         case 16: return launch_bwd_fused_t<16, 1, 12, 1, 2, false>(p, a, n_js_out, st);

@@ -330,337 +330,6 @@ __global__ void bwd_prep_kernel(const float* __restrict__ g_log_qz, const float*
     }
 }
 
-template <int VEC> struct VecLoad;
-template <> struct VecLoad<1> { static __device__ __forceinline__ void ld(const float* p, float (&v)[1]) { v[0] = *p; } };
-template <> struct VecLoad<2> { static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) {
-    const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; } };
-template <> struct VecLoad<4> { static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
-    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } };
-
-// element update shared by both backward sweeps; returns r (masked coefficient) and dl
-template <bool kWeighted>
-__device__ __forceinline__ void bwd_element(float mu, float zs, float ns, float qmx, float gps, float gq, float rho,
-                                            float& r, float& dl, float& qc) {
-    dl = fmaf(mu, ns, zs);
-    const float q = dl * dl;
-    qc = fmin_nan(q, qmx);
-    float e = ex2(-qc);
-    if (kWeighted) e *= rho;
-    const float coef = fmaf(e, gps, gq);
-    r = (q > qmx) ? 0.0f : coef;
-}
-
-template <int DPT, int RI>
-__global__ void __launch_bounds__(kBwdWarps * 32, 2)
-tc_bwd_row_kernel(const BwdRowArgs a) {
-    constexpr int VEC = DPT < 4 ? DPT : 4;
-    constexpr int NCH = DPT / VEC;
-    constexpr int DP = 32 * DPT;
-    constexpr int CH = 32 * VEC;                                             // dims per chunk
-    constexpr int JT = (kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP);
-    constexpr int TILE = JT * DP;
-    constexpr int ROWS = kBwdWarps * RI;
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* mu_tiles = reinterpret_cast<float*>(smem_raw);                    // [kStages][TILE]
-    float* s2_tiles = mu_tiles + (size_t)kStages * TILE;                     // [kStages][ROWS][JT]
-    float* gq_buf = s2_tiles + (size_t)kStages * ROWS * JT;                  // [kBwdWarps][RI][JT]
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gq_buf + (size_t)kBwdWarps * RI * JT);
-    uint64_t* bar_empty = bar_full + kStages;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * ROWS + warp * RI;                          // first of this warp's RI rows
-
-    float zs[RI][DPT], ns[RI][DPT], qmx[RI][DPT], gps[RI][DPT], A[RI][DPT], CR[RI][DPT];
-    float gJ[RI], J2[RI];
-#pragma unroll
-    for (int r = 0; r < RI; ++r) {
-        const size_t base = (size_t)(row0 + r) * DP;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            float v[VEC];
-            VecLoad<VEC>::ld(a.zs + base + c * CH + VEC * lane, v);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) zs[r][c * VEC + e] = v[e];
-            VecLoad<VEC>::ld(a.ns + base + c * CH + VEC * lane, v);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) ns[r][c * VEC + e] = v[e];
-            VecLoad<VEC>::ld(a.qmax + base + c * CH + VEC * lane, v);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) qmx[r][c * VEC + e] = v[e];
-            VecLoad<VEC>::ld(a.gps + base + c * CH + VEC * lane, v);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) gps[r][c * VEC + e] = v[e];
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) { A[r][c * VEC + e] = 0.0f; CR[r][c * VEC + e] = 0.0f; }
-        }
-        gJ[r] = a.gj[row0 + r];
-        J2[r] = a.J2[row0 + r];
-    }
-
-    const int j0 = blockIdx.y * a.js_len;
-    const int j1 = min(a.bg_pad, j0 + a.js_len);
-    const int ntiles = (j1 - j0) / JT;
-    constexpr uint32_t kTxBytes = (TILE + ROWS * JT) * sizeof(float);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kBwdWarps); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    auto issue = [&](int t) {                                                // warp 0, all lanes
-        const int sn = t % kStages;
-        if (lane == 0) {
-            if (t >= kStages) mbar_wait(&bar_empty[sn], ((t / kStages) - 1) & 1);
-            mbar_arrive_expect_tx(&bar_full[sn], kTxBytes);
-            bulk_g2s(mu_tiles + (size_t)sn * TILE, a.mu_pad + (size_t)(j0 + t * JT) * DP, TILE * sizeof(float), &bar_full[sn]);
-        }
-        __syncwarp();
-        for (int r = lane; r < ROWS; r += 32)
-            bulk_g2s(s2_tiles + ((size_t)sn * ROWS + r) * JT,
-                     a.s2 + (size_t)(blockIdx.x * ROWS + r) * a.ld_s2 + (j0 + t * JT), JT * sizeof(float), &bar_full[sn]);
-    };
-    if (warp == 0 && ntiles > 0) issue(0);
-
-    float* gq = gq_buf + (size_t)warp * RI * JT;
-    for (int t = 0; t < ntiles; ++t) {
-        const int st = t % kStages;
-        if (warp == 0 && t + 1 < ntiles) issue(t + 1);
-        mbar_wait(&bar_full[st], (t / kStages) & 1);
-        const float* tile = mu_tiles + (size_t)st * TILE;
-        const float* s2t = s2_tiles + ((size_t)st * ROWS + warp * RI) * JT;
-        const int jt0 = j0 + t * JT;
-        const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
-
-        // joint-term coefficients gJ_i * q_ij of this warp's rows for the tile (4 per lane)
-        __syncwarp();
-        for (int idx = lane; idx < RI * JT; idx += 32) {
-            const int r = idx / JT, jj = idx % JT;
-            float rho = 1.0f, l2 = 0.0f;
-            if (special) weight_of(a.w, a.row_offset + row0 + r, jt0 + jj, rho, l2);
-            float gjr = gJ[0], j2r = J2[0];
-#pragma unroll
-            for (int rr = 1; rr < RI; ++rr) if (r == rr) { gjr = gJ[rr]; j2r = J2[rr]; }
-            const float qv = ex2(l2 - s2t[idx] - j2r);
-            gq[idx] = (jt0 + jj < a.w.b_glob) ? gjr * qv : 0.0f;
-        }
-        __syncwarp();
-
-        for (int jj = 0; jj < JT; jj += 4) {
-            float gq4[RI][4];
-#pragma unroll
-            for (int r = 0; r < RI; ++r) {
-                const float4 t4 = *reinterpret_cast<const float4*>(gq + r * JT + jj);
-                gq4[r][0] = t4.x; gq4[r][1] = t4.y; gq4[r][2] = t4.z; gq4[r][3] = t4.w;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float mu[DPT];
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    float v[VEC];
-                    VecLoad<VEC>::ld(tile + (jj + u) * DP + c * CH + VEC * lane, v);
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) mu[c * VEC + e] = v[e];
-                }
-#pragma unroll
-                for (int r = 0; r < RI; ++r) {
-                    float rho = 1.0f, l2 = 0.0f;
-                    if (special) weight_of(a.w, a.row_offset + row0 + r, jt0 + jj + u, rho, l2);
-#pragma unroll
-                    for (int e = 0; e < DPT; ++e) {
-                        float rr, dl, qc;
-                        if (special) bwd_element<true>(mu[e], zs[r][e], ns[r][e], qmx[r][e], gps[r][e], gq4[r][u], rho, rr, dl, qc);
-                        else         bwd_element<false>(mu[e], zs[r][e], ns[r][e], qmx[r][e], gps[r][e], gq4[r][u], rho, rr, dl, qc);
-                        A[r][e] = fmaf(rr, dl, A[r][e]);
-                        CR[r][e] = fmaf(rr, fmaf(qc, kTwoLn2, -1.0f), CR[r][e]);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_empty[st]);
-    }
-
-#pragma unroll
-    for (int r = 0; r < RI; ++r) {
-        const size_t base = ((size_t)blockIdx.y * a.bl_pad + row0 + r) * DP;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                a.Apart[base + c * CH + VEC * lane + e] = A[r][c * VEC + e];
-                a.CRpart[base + c * CH + VEC * lane + e] = CR[r][c * VEC + e];
-            }
-        }
-    }
-}
-
-template <int DPT, int RJ>
-__global__ void __launch_bounds__(kBwdWarps * 32, 2)
-tc_bwd_col_kernel(const BwdColArgs a) {
-    constexpr int VEC = DPT < 4 ? DPT : 4;
-    constexpr int NCH = DPT / VEC;
-    constexpr int DP = 32 * DPT;
-    constexpr int CH = 32 * VEC;
-    constexpr int IT = (2048 / DP) < 4 ? 4 : ((2048 / DP) > 16 ? 16 : (2048 / DP));
-    constexpr int RT = IT * DP;                                              // floats per row-array tile
-    constexpr int COLS = kBwdWarps * RJ;
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* row_tiles = reinterpret_cast<float*>(smem_raw);                   // [kStages][4][RT]  zs, ns, qmax, gps
-    float* s2_tiles = row_tiles + (size_t)kStages * 4 * RT;                  // [kStages][IT][COLS]
-    float* sc_tiles = s2_tiles + (size_t)kStages * IT * COLS;                // [kStages][2][IT]  gJ, J2
-    float* gq_buf = sc_tiles + (size_t)kStages * 2 * IT;                     // [kBwdWarps][IT][RJ]
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(gq_buf + (size_t)kBwdWarps * IT * RJ);
-    uint64_t* bar_empty = bar_full + kStages;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int col0 = blockIdx.x * COLS + warp * RJ;                          // first of this warp's RJ columns
-
-    float mu[RJ][DPT], G[RJ][DPT];
-#pragma unroll
-    for (int c2 = 0; c2 < RJ; ++c2) {
-        const size_t base = (size_t)(col0 + c2) * DP;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            float v[VEC];
-            VecLoad<VEC>::ld(a.mu_pad + base + c * CH + VEC * lane, v);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) { mu[c2][c * VEC + e] = v[e]; G[c2][c * VEC + e] = 0.0f; }
-        }
-    }
-
-    const int i0 = blockIdx.y * a.is_len;
-    const int i1 = min(a.bl_pad, i0 + a.is_len);
-    const int ntiles = (i1 - i0) / IT;
-    constexpr uint32_t kTxBytes = (4 * RT + IT * COLS + 2 * IT) * sizeof(float);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kBwdWarps); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    auto issue = [&](int t) {                                                // warp 0, all lanes
-        const int sn = t % kStages;
-        const int it0 = i0 + t * IT;
-        if (lane == 0) {
-            if (t >= kStages) mbar_wait(&bar_empty[sn], ((t / kStages) - 1) & 1);
-            mbar_arrive_expect_tx(&bar_full[sn], kTxBytes);
-            float* dst = row_tiles + (size_t)sn * 4 * RT;
-            bulk_g2s(dst + 0 * RT, a.zs + (size_t)it0 * DP, RT * sizeof(float), &bar_full[sn]);
-            bulk_g2s(dst + 1 * RT, a.ns + (size_t)it0 * DP, RT * sizeof(float), &bar_full[sn]);
-            bulk_g2s(dst + 2 * RT, a.qmax + (size_t)it0 * DP, RT * sizeof(float), &bar_full[sn]);
-            bulk_g2s(dst + 3 * RT, a.gps + (size_t)it0 * DP, RT * sizeof(float), &bar_full[sn]);
-            bulk_g2s(sc_tiles + (size_t)sn * 2 * IT, a.gj + it0, IT * sizeof(float), &bar_full[sn]);
-            bulk_g2s(sc_tiles + (size_t)sn * 2 * IT + IT, a.J2 + it0, IT * sizeof(float), &bar_full[sn]);
-        }
-        __syncwarp();
-        for (int r = lane; r < IT; r += 32)
-            bulk_g2s(s2_tiles + ((size_t)sn * IT + r) * COLS,
-                     a.s2 + (size_t)(it0 + r) * a.ld_s2 + blockIdx.x * COLS, COLS * sizeof(float), &bar_full[sn]);
-    };
-    if (warp == 0 && ntiles > 0) issue(0);
-
-    const bool special = a.w.mss && (col0 < 2);                              // this warp owns column 0 and/or 1
-    float* gq = gq_buf + (size_t)warp * IT * RJ;
-
-    for (int t = 0; t < ntiles; ++t) {
-        const int st = t % kStages;
-        if (warp == 0 && t + 1 < ntiles) issue(t + 1);
-        mbar_wait(&bar_full[st], (t / kStages) & 1);
-        const float* rt = row_tiles + (size_t)st * 4 * RT;
-        const float* s2t = s2_tiles + (size_t)st * IT * COLS + warp * RJ;
-        const float* sct = sc_tiles + (size_t)st * 2 * IT;
-        const int it0 = i0 + t * IT;
-
-        __syncwarp();
-        for (int idx = lane; idx < IT * RJ; idx += 32) {
-            const int ii = idx / RJ, c2 = idx % RJ;
-            float rho = 1.0f, l2 = 0.0f;
-            if (special) weight_of(a.w, a.row_offset + it0 + ii, col0 + c2, rho, l2);
-            const float qv = ex2(l2 - s2t[ii * COLS + c2] - sct[IT + ii]);
-            gq[idx] = (col0 + c2 < a.w.b_glob && it0 + ii < a.b_loc) ? sct[ii] * qv : 0.0f;
-        }
-        __syncwarp();
-
-        for (int ii = 0; ii < IT; ++ii) {
-            float zs[DPT], ns[DPT], qmx[DPT], gps[DPT];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                float v[VEC];
-                const int off = ii * DP + c * CH + VEC * lane;
-                VecLoad<VEC>::ld(rt + 0 * RT + off, v);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) zs[c * VEC + e] = v[e];
-                VecLoad<VEC>::ld(rt + 1 * RT + off, v);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) ns[c * VEC + e] = v[e];
-                VecLoad<VEC>::ld(rt + 2 * RT + off, v);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) qmx[c * VEC + e] = v[e];
-                VecLoad<VEC>::ld(rt + 3 * RT + off, v);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) gps[c * VEC + e] = v[e];
-            }
-            float gqv[RJ];
-#pragma unroll
-            for (int c2 = 0; c2 < RJ; ++c2) gqv[c2] = gq[ii * RJ + c2];
-#pragma unroll
-            for (int c2 = 0; c2 < RJ; ++c2) {
-                float rho = 1.0f, l2 = 0.0f;
-                if (special) weight_of(a.w, a.row_offset + it0 + ii, col0 + c2, rho, l2);
-#pragma unroll
-                for (int e = 0; e < DPT; ++e) {
-                    float rr, dl, qc;
-                    if (special) bwd_element<true>(mu[c2][e], zs[e], ns[e], qmx[e], gps[e], gqv[c2], rho, rr, dl, qc);
-                    else         bwd_element<false>(mu[c2][e], zs[e], ns[e], qmx[e], gps[e], gqv[c2], rho, rr, dl, qc);
-                    G[c2][e] = fmaf(rr * dl, ns[e], G[c2][e]);
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_empty[st]);
-    }
-
-#pragma unroll
-    for (int c2 = 0; c2 < RJ; ++c2) {
-        const size_t base = ((size_t)blockIdx.y * a.bg_pad + col0 + c2) * DP;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) a.Gpart[base + c * CH + VEC * lane + e] = G[c2][c * VEC + e];
-        }
-    }
-}
-
-__global__ void bwd_finalize_kernel(const BwdFinArgs a) {
-    const int64_t n_row = (int64_t)a.b_loc * a.d;
-    const int64_t n_col = (int64_t)a.b_glob * a.d;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_row + n_col; idx += (int64_t)gridDim.x * blockDim.x) {
-        if (idx < n_row) {
-            const int i = (int)(idx / a.d), dd = (int)(idx % a.d);
-            const size_t o = (size_t)i * a.dp + dd;
-            float sa = 0.0f, sc = 0.0f;
-            for (int s = 0; s < a.n_js; ++s) {
-                sa += a.Apart[(size_t)s * a.bl_pad * a.dp + o];
-                sc += a.CRpart[(size_t)s * a.bl_pad * a.dp + o];
-            }
-            a.grad_z[(int64_t)i * a.ldgz + dd] = kTwoLn2 * a.ns[o] * sa;
-            a.grad_lv[(int64_t)i * a.ldglv + dd] = a.vr[o] * sc;
-        } else {
-            const int64_t k = idx - n_row;
-            const int j = (int)(k / a.d), dd = (int)(k % a.d);
-            const size_t o = (size_t)j * a.dp + dd;
-            float sg = 0.0f;
-            for (int s = 0; s < a.n_is; ++s) sg += a.Gpart[(size_t)s * a.bg_pad * a.dp + o];
-            a.grad_mu[(int64_t)j * a.ldgmu + dd] = -kTwoLn2 * sg;
-        }
-    }
-}
-
 // =====================================================================================================
 // Launchers
 // =====================================================================================================
@@ -727,71 +396,6 @@ cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g
     LaunchScope scope(kKernNone, st);
     bwd_prep_kernel<<<grid_for(total, 256), 256, 0, st>>>(g_log_qz, g_log_qz_prod, g_loss, g_kl, beta, S, p.b_loc, p.bl_pad, p.dp,
                                                            gps, gj, gk, zero, (int64_t)zero_n);
-    return cudaGetLastError();
-}
-
-template <int DPT, int RI>
-static cudaError_t launch_bwd_row_t(const Plan& p, const BwdRowArgs& a, cudaStream_t st) {
-    constexpr int DP = 32 * DPT;
-    constexpr int JT = (kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP);
-    constexpr int ROWS = kBwdWarps * RI;
-    const size_t smem = ((size_t)kStages * JT * DP + (size_t)kStages * ROWS * JT + (size_t)kBwdWarps * RI * JT) * sizeof(float)
-                        + 2 * kStages * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_bwd_row_kernel<DPT, RI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    LaunchScope scope(kKernBwdRow, st);
-    tc_bwd_row_kernel<DPT, RI><<<dim3(p.n_rb_bwr, p.n_js_bwr), kBwdWarps * 32, smem, st>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_bwd_row(const Plan& p, const BwdRowArgs& a, cudaStream_t st) {
-    switch (p.dpt) {
-        case 1:  return launch_bwd_row_t<1, 4>(p, a, st);
-        case 2:  return launch_bwd_row_t<2, 4>(p, a, st);
-        case 4:  return launch_bwd_row_t<4, 4>(p, a, st);
-        case 8:  return launch_bwd_row_t<8, 2>(p, a, st);
-        case 16: return launch_bwd_row_t<16, 1>(p, a, st);
-        default: return cudaErrorInvalidValue;
-    }
-}
-
-template <int DPT, int RJ>
-static cudaError_t launch_bwd_col_t(const Plan& p, const BwdColArgs& a, cudaStream_t st) {
-    constexpr int DP = 32 * DPT;
-    constexpr int IT = (2048 / DP) < 4 ? 4 : ((2048 / DP) > 16 ? 16 : (2048 / DP));
-    constexpr int COLS = kBwdWarps * RJ;
-    const size_t smem = ((size_t)kStages * 4 * IT * DP + (size_t)kStages * IT * COLS + (size_t)kStages * 2 * IT
-                         + (size_t)kBwdWarps * IT * RJ) * sizeof(float) + 2 * kStages * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_bwd_col_kernel<DPT, RJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    LaunchScope scope(kKernBwdCol, st);
-    tc_bwd_col_kernel<DPT, RJ><<<dim3(p.n_cb, p.n_is), kBwdWarps * 32, smem, st>>>(a);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_bwd_col(const Plan& p, const BwdColArgs& a, cudaStream_t st) {
-    switch (p.dpt) {
-        case 1:  return launch_bwd_col_t<1, 8>(p, a, st);
-        case 2:  return launch_bwd_col_t<2, 8>(p, a, st);
-        case 4:  return launch_bwd_col_t<4, 8>(p, a, st);
-        case 8:  return launch_bwd_col_t<8, 4>(p, a, st);
-        case 16: return launch_bwd_col_t<16, 2>(p, a, st);
-        default: return cudaErrorInvalidValue;
-    }
-}
-
-cudaError_t launch_bwd_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st) {
-    const int64_t n = (int64_t)p.b_loc * p.d + (int64_t)p.b_glob * p.d;
-    LaunchScope scope(kKernNone, st);
-    bwd_finalize_kernel<<<grid_for(n, 256), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -27,26 +27,6 @@ struct FinArgs {
     float beta; float* loss_rows; float* kl_rows;
 };
 
-struct BwdRowArgs {
-    const float* zs; const float* ns; const float* qmax; const float* gps;   // [bl_pad][dp]
-    const float* gj; const float* J2;                                        // [bl_pad]
-    const float* mu_pad;                                                     // [bg_pad][dp]
-    const float* s2; int64_t ld_s2;
-    float* Apart; float* CRpart;                                             // [n_js][bl_pad][dp]
-    int b_loc, bl_pad, bg_pad, row_offset, js_len;
-    Weights w;
-};
-
-struct BwdColArgs {
-    const float* zs; const float* ns; const float* qmax; const float* gps;
-    const float* gj; const float* J2;
-    const float* mu_pad;
-    const float* s2; int64_t ld_s2;
-    float* Gpart;                                                            // [n_is][bg_pad][dp]
-    int b_loc, bl_pad, bg_pad, row_offset, is_len;
-    Weights w;
-};
-
 struct BwdFusedArgs {
     const float* zs; const float* ns; const float* qmax; const float* gps;   // [bl_pad][dp]
     const float* gj; const float* J2;                                        // [bl_pad]
@@ -77,9 +57,6 @@ cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st
 // writes gps = gP/S, gj = gJ, gk = g_loss + g_kl (if gk != null) and zeroes `zero_n` floats at `zero` (the column accumulator).
 cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g_log_qz_prod, const float* g_loss, const float* g_kl,
                             float beta, const float* S, float* gps, float* gj, float* gk, float* zero, size_t zero_n, cudaStream_t st);
-cudaError_t launch_bwd_row(const Plan& p, const BwdRowArgs& a, cudaStream_t st);
-cudaError_t launch_bwd_col(const Plan& p, const BwdColArgs& a, cudaStream_t st);
-cudaError_t launch_bwd_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st);
 cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out, cudaStream_t st);
 void set_bwd_variant(int v);
 // column-variance ("full" path) variant, tc_colvar.cu

@@ -20,12 +20,8 @@ struct Plan {
     int d, dp, dpt;            // dp = power of two >= max(d, 32); dpt = dp / 32 (floats per lane / lanes per row)
     int b_loc, b_glob, bl_pad, bg_pad;
     int jt;                    // column-tile height (rows of mu per stage) = kTileFloats / dp
-    // forward / backward-row pass: grid (n_rb, n_js)
+    // forward sweep: grid (n_rb_fwd, n_js_fwd)
     int fwd_rows, n_rb_fwd, n_js_fwd, js_len_fwd;
-    int bwr_rows, bwr_ri, n_rb_bwr, n_js_bwr, js_len_bwr;
-    int bwf_rows, n_js_bwf, js_len_bwf;   // fused backward sweep: 12 warps x bwr_ri rows per CTA, one CTA per SM
-    // backward-column pass: grid (n_cb, n_is)
-    int bwc_cols, bwc_rj, bwc_it, n_cb, n_is, is_len;
     // workspace (byte offsets)
     size_t off_mu, off_zs, off_ns, off_qmax, off_shift, off_vr;   // [bg_pad|bl_pad][dp]
     size_t off_S, off_J2;                                         // persistent forward results
@@ -79,21 +75,8 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.fwd_rows = kFwdWarps * (32 / p.dpt);
     p.n_rb_fwd = p.bl_pad / p.fwd_rows;
     choose_splits(p.n_rb_fwd, sms * 3, p.bg_pad, p.jt, 4, p.n_js_fwd, p.js_len_fwd);   // 3 resident CTAs per SM
-    // ---- backward row pass (row-local gradients)
-    p.bwr_ri = p.dpt >= 16 ? 1 : (p.dpt >= 8 ? 2 : 4);
-    p.bwr_rows = kBwdWarps * p.bwr_ri;
-    p.n_rb_bwr = p.bl_pad / p.bwr_rows;
-    choose_splits(p.n_rb_bwr, sms * 2, p.bg_pad, p.jt, 4, p.n_js_bwr, p.js_len_bwr);
-    // ---- fused backward sweep
-    p.bwf_rows = 12 * p.bwr_ri;          // default variant; the launcher re-plans for the variant it runs
+    // ---- fused backward sweep: its launcher plans the column split for the CTA shape it runs (<= kMaxSplits)
     p.sms = sms;
-    p.n_js_bwf = kMaxSplits; p.js_len_bwf = 0;
-    // ---- backward column pass (grad_mu): a CTA owns bwc_cols columns and a range of is_len rows
-    p.bwc_rj = p.dpt >= 16 ? 2 : (p.dpt >= 8 ? 4 : 8);
-    p.bwc_cols = kBwdWarps * p.bwc_rj;
-    p.bwc_it = 2048 / dp; if (p.bwc_it < 4) p.bwc_it = 4; if (p.bwc_it > 16) p.bwc_it = 16;
-    p.n_cb = p.bg_pad / p.bwc_cols;
-    choose_splits(p.n_cb, sms * 2, p.bl_pad, p.bwc_it, 4, p.n_is, p.is_len);
 
     // ---- workspace
     size_t off = 0;
@@ -117,10 +100,9 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.boff_gps = b; b = align256(b + row_arr);
     p.boff_gj = b;  b = align256(b + (size_t)p.bl_pad * sizeof(float));
     p.boff_gk = b;  b = align256(b + (size_t)p.bl_pad * sizeof(float));
-    const int n_js_max = p.n_js_bwr > p.n_js_bwf ? p.n_js_bwr : p.n_js_bwf;
-    p.boff_A = b;   b = align256(b + (size_t)n_js_max * row_arr);
-    p.boff_CR = b;  b = align256(b + (size_t)n_js_max * row_arr);
-    p.boff_G = b;   b = align256(b + (size_t)(p.n_is > 2 ? p.n_is : 2) * col_arr);
+    p.boff_A = b;   b = align256(b + (size_t)kMaxSplits * row_arr);          // row-local partial sums per column split
+    p.boff_CR = b;  b = align256(b + (size_t)kMaxSplits * row_arr);
+    p.boff_G = b;   b = align256(b + 2 * col_arr);                           // column accumulators (mu [, logvar])
     p.bwd_bytes = b;
     return true;
 }
