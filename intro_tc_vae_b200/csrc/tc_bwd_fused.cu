@@ -251,6 +251,10 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * ROWS + warp * RI;
+    // A CTA covers DP dims starting at d0 of rows whose pitch is a.pitch floats: for D > 128 the grid's z dimension walks
+    // 128-dim slices (row-local sums and column sums are independent per dim; only the joint coefficients are shared).
+    const int pitch = a.pitch;
+    const int d0 = blockIdx.z * DP;
 
     // ---- row constants and accumulators of this warp's RI rows (this lane's dims) -> registers.
     //      Rows past the padded batch are clamped for loads and carry zero coefficients.
@@ -259,7 +263,7 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
         const bool valid = (row0 + r) < a.bl_pad;
-        const size_t base = (size_t)min(row0 + r, a.bl_pad - 1) * DP;
+        const size_t base = (size_t)min(row0 + r, a.bl_pad - 1) * pitch + d0;
         float vz[DPT], vn[DPT], vq[DPT], vg[DPT];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -306,9 +310,15 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
         if (lane == 0) {
             if (t >= kStages) mbar_wait(&bar_empty[sn], ((t / kStages) - 1) & 1);
             mbar_arrive_expect_tx(&bar_full[sn], kTxBytes);
-            bulk_g2s(mu_tiles + (size_t)sn * TILE, a.mu_pad + (size_t)(j0 + t * JT) * DP, TILE * sizeof(float), &bar_full[sn]);
+            if (pitch == DP)                                                 // whole rows: one contiguous bulk copy
+                bulk_g2s(mu_tiles + (size_t)sn * TILE, a.mu_pad + (size_t)(j0 + t * JT) * DP, TILE * sizeof(float), &bar_full[sn]);
         }
         __syncwarp();
+        if (pitch != DP) {                                                   // a 128-dim slice of wider rows: one copy per column
+            for (int c = lane; c < JT; c += 32)
+                bulk_g2s(mu_tiles + (size_t)sn * TILE + (size_t)c * DP, a.mu_pad + (size_t)(j0 + t * JT + c) * pitch + d0,
+                         DP * sizeof(float), &bar_full[sn]);
+        }
         for (int r = lane; r < ROWS; r += 32)
             bulk_g2s(s2_tiles + ((size_t)sn * ROWS + r) * JT,
                      a.s2 + (size_t)min((int)(blockIdx.x * ROWS + r), a.bl_pad - 1) * a.ld_s2 + (j0 + t * JT), JT * sizeof(float), &bar_full[sn]);
@@ -329,7 +339,7 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
                 const float4 v = *reinterpret_cast<const float4*>(gsb + ((size_t)w * JS + col) * DP + 4 * chunk);
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
-            red_add_v4(a.Gacc + (size_t)(col0 + col) * DP + 4 * chunk, acc.x, acc.y, acc.z, acc.w);
+            red_add_v4(a.Gacc + (size_t)(col0 + col) * pitch + d0 + 4 * chunk, acc.x, acc.y, acc.z, acc.w);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&g_empty[b]);
@@ -381,7 +391,7 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
 #pragma unroll
     for (int r = 0; r < RI; ++r) {
         if (row0 + r >= a.bl_pad) continue;
-        const size_t base = ((size_t)blockIdx.y * a.bl_pad + row0 + r) * DP;
+        const size_t base = ((size_t)blockIdx.y * a.bl_pad + row0 + r) * pitch + d0;
         float va[DPT], vc[DPT];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
@@ -463,11 +473,13 @@ static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, int* n_js_o
     }
     const int n_rb = (p.bl_pad + ROWS - 1) / ROWS;
     int n_js, js_len;
-    choose_splits(n_rb, p.sms * ctas_per_sm, p.bg_pad, p.jt, 4, n_js, js_len);
+    choose_splits(n_rb * (p.dp / GEO::DP), p.sms * ctas_per_sm, p.bg_pad, GEO::JT, 4, n_js, js_len);
     a.js_len = js_len;
+    a.pitch = p.dp;
     *n_js_out = n_js;
+    const int n_slices = p.dp / GEO::DP;                                      // 1 unless a wide latent is walked in 128-dim slices
     LaunchScope scope(kKernBwdRow, st);
-    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR><<<dim3(n_rb, n_js), NW * 32, smem, st>>>(a);
+    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR><<<dim3(n_rb, n_js, n_slices), NW * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -488,8 +500,8 @@ cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out
                 case 22: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 3>(p, a, n_js_out, st);       // ablation: no joint-coefficient loads
                 default: return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);             // best of the sweep
             }
-        case 8:  return launch_bwd_fused_t<8, 2, 12, 1, 4, false>(p, a, n_js_out, st);
-        case 16: return launch_bwd_fused_t<16, 1, 12, 1, 2, false>(p, a, n_js_out, st);
+        case 8: case 16:                             // D = 256 / 512: the tuned 128-dim kernel over 2 / 4 slices (grid.z)
+            return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -36,6 +36,7 @@ struct BwdFusedArgs {
     float* Gacc;                                                             // [bg_pad][dp], zeroed by the caller
     float* Gacc2;                                                            // column-variance variant: logvar column sums
     int b_loc, bl_pad, bg_pad, row_offset, js_len;
+    int pitch;                                                               // floats per row of the [*, dp] arrays
     Weights w;
 };
 
