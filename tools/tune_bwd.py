@@ -15,7 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--zdim", type=int, default=128)
-    ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,8,9,10")
+    ap.add_argument("--variants", default="-1,0,1,2,4,11,30,20,21,22")
     ap.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
     lib = _lib.load()
