@@ -114,6 +114,7 @@ def _(z, mu_all, logvar, row_offset, dataset_size, flags, g_log_qz, g_log_qz_pro
 
 
 def _tc_setup_context(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
     z, mu_all, logvar, row_offset, dataset_size, flags = inputs
     _, _, ws = output
     ctx.save_for_backward(z, mu_all, logvar, ws)
@@ -125,6 +126,8 @@ def _tc_autograd_backward(ctx, g_log_qz, g_log_qz_prod, _g_ws):
     row_offset, dataset_size, flags = ctx.meta
     if not flags & _lib.SAVE_FOR_BACKWARD:
         raise RuntimeError("tcelbo: forward ran without TCELBO_SAVE_FOR_BACKWARD but a gradient was requested")
+    if g_log_qz is None and g_log_qz_prod is None:
+        return None, None, None, None, None, None
     if g_log_qz is None:
         g_log_qz = torch.zeros(z.shape[0], dtype=torch.float32, device=z.device)
     if g_log_qz_prod is None:
@@ -198,6 +201,7 @@ def _(z, mu_all, logvar, row_offset, dataset_size, flags, beta, g_loss, g_kl, g_
 
 
 def _klloss_setup_context(ctx, inputs, output):
+    ctx.set_materialize_grads(False)          # unused outputs arrive as None instead of zero-filled tensors
     z, mu_all, logvar, row_offset, dataset_size, flags, beta = inputs
     ctx.save_for_backward(z, mu_all, logvar, output[4])
     ctx.meta = (row_offset, dataset_size, flags, beta)
@@ -208,6 +212,8 @@ def _klloss_autograd_backward(ctx, g_loss, g_kl, g_log_qz, g_log_qz_prod, _g_ws)
     row_offset, dataset_size, flags, beta = ctx.meta
     if not flags & _lib.SAVE_FOR_BACKWARD:
         raise RuntimeError("tcelbo: forward ran without TCELBO_SAVE_FOR_BACKWARD but a gradient was requested")
+    if g_loss is None and g_kl is None and g_log_qz is None and g_log_qz_prod is None:
+        return None, None, None, None, None, None, None
     if g_loss is None:
         g_loss = torch.zeros(z.shape[0], dtype=torch.float32, device=z.device)
     gz, gmu, glv = _klloss_backward(z, mu_all, logvar, row_offset, dataset_size, flags, beta,
