@@ -153,6 +153,25 @@ int tcelbo_rowdensity_backward(const float* x, int64_t ldx, const float* mu, int
                                float* grad_x, int64_t ldgx, float* grad_mu, int64_t ldgmu,
                                float* grad_logvar, int64_t ldglv, void* stream);
 
+/*
+ * Materialised-tensor helpers kept for API parity with the reference's ops.py (HBM-bound; the fused ops above never
+ * build the tensor).  Densities: out[i,j,d] over a broadcast 3-D index space, operand strides in elements (0 on
+ * broadcast dims); floored != 0 selects gaussian_log_density_torch (ops.py:15-21), else gaussian_log_density
+ * (ops.py:24-29).  `shape`, `sx`, `sm`, `sl` are HOST arrays of three int64.  The backward writes elementwise
+ * gradients at the broadcast shape (the caller reduces them over broadcast dims).
+ */
+int tcelbo_density_forward(int floored, const float* x, const float* mu, const float* logvar, const int64_t* shape,
+                           const int64_t* sx, const int64_t* sm, const int64_t* sl, float* out, void* stream);
+int tcelbo_density_backward(int floored, const float* x, const float* mu, const float* logvar, const float* g, const int64_t* shape,
+                            const int64_t* sx, const int64_t* sm, const int64_t* sl, float* gx, float* gmu, float* glv, void* stream);
+/* minibatch_stratified_sampling / minibatch_weighted_sampling (ops.py:104-115 / 92-101) on a contiguous [b,b,d] tensor;
+ * lse_dim [b,d] and pair_sums [b,b] are saved for the backward. */
+int tcelbo_sampling_forward(const float* log_qz_prob, int b, int d, int64_t dataset_size, uint32_t flags,
+                            float* log_qz_prod, float* log_qz, float* lse_dim, float* pair_sums, void* stream);
+int tcelbo_sampling_backward(const float* log_qz_prob, int b, int d, int64_t dataset_size, uint32_t flags,
+                             const float* g_log_qz_prod, const float* g_log_qz, const float* lse_dim, const float* pair_sums,
+                             const float* log_qz, float* grad_log_qz_prob, void* stream);
+
 /* ---- diagnostics used by bench.py (no reference counterpart) --------------------------------------- */
 /* Number of kernels this library has launched in the calling process so far. */
 long long tcelbo_launch_count(void);

@@ -46,6 +46,12 @@ _SIGNATURES = {
     "tcelbo_rowdensity_forward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_void_p]),
     "tcelbo_rowdensity_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, _f, c_int, c_int,
                                            _f, c_int64, _f, c_int64, _f, c_int64, c_void_p]),
+    "tcelbo_density_forward": (c_int, [c_int, _f, _f, _f, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
+                                       _f, c_void_p]),
+    "tcelbo_density_backward": (c_int, [c_int, _f, _f, _f, _f, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
+                                        POINTER(c_int64), _f, _f, _f, c_void_p]),
+    "tcelbo_sampling_forward": (c_int, [_f, c_int, c_int, c_int64, c_uint32, _f, _f, _f, _f, c_void_p]),
+    "tcelbo_sampling_backward": (c_int, [_f, c_int, c_int, c_int64, c_uint32, _f, _f, _f, _f, _f, _f, c_void_p]),
     "tcelbo_launch_count": (ctypes.c_longlong, []),
     "tcelbo_profile_events": (c_int, [c_int, c_void_p, c_void_p]),
     "tcelbo_set_tuning": (c_int, [c_char_p, c_int]),

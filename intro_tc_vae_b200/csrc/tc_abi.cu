@@ -8,6 +8,7 @@
 
 #include "tc_instr.h"
 #include "tc_kernels.h"
+#include "tc_materialized.h"
 #include "tc_rowops.h"
 #include "tcelbo.h"
 
@@ -332,6 +333,54 @@ int tcelbo_rowdensity_backward(const float* x, int64_t ldx, const float* mu, int
     cudaError_t e = launch_rowdensity_bwd(x, ldx, mu, ldmu, logvar, ldlv, g_rows, b, d, grad_x, ldgx, grad_mu, ldgmu,
                                           grad_logvar, ldglv, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "rowdensity_bwd");
+}
+
+int tcelbo_density_forward(int floored, const float* x, const float* mu, const float* logvar, const int64_t* shape,
+                           const int64_t* sx, const int64_t* sm, const int64_t* sl, float* out, void* stream) {
+    ROWOP_CHECK(x && mu && logvar && out && shape && sx && sm && sl, "null pointer");
+    ROWOP_CHECK(shape[0] >= 1 && shape[1] >= 1 && shape[2] >= 1, "bad shape");
+    cudaError_t e = launch_density_fwd(floored != 0, x, mu, logvar, shape, sx, sm, sl, out, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "density_fwd");
+}
+
+int tcelbo_density_backward(int floored, const float* x, const float* mu, const float* logvar, const float* g, const int64_t* shape,
+                            const int64_t* sx, const int64_t* sm, const int64_t* sl, float* gx, float* gmu, float* glv, void* stream) {
+    ROWOP_CHECK(x && mu && logvar && g && gx && gmu && glv && shape && sx && sm && sl, "null pointer");
+    cudaError_t e = launch_density_bwd(floored != 0, x, mu, logvar, g, shape, sx, sm, sl, gx, gmu, glv, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "density_bwd");
+}
+
+namespace {
+void sampling_weights(int b, int64_t n, uint32_t flags, Weights& w, float& lw_n, float& lw_s, float& post) {
+    w = make_weights(b, n, flags);
+    lw_n = lw_s = 0.0f; post = 0.0f;
+    if (flags & TCELBO_EST_MWS) { post = w.lw_u; return; }                    // subtract log(B*N) after the logsumexp
+    const double m = (double)(b - 1);
+    lw_n = logf((float)(1.0 / (double)n));
+    lw_s = logf((float)(((double)n - m) / ((double)n * m)));                  // NaN when N < B-1, like the reference
+}
+}  // namespace
+
+int tcelbo_sampling_forward(const float* log_qz_prob, int b, int d, int64_t dataset_size, uint32_t flags,
+                            float* log_qz_prod, float* log_qz, float* lse_dim, float* pair_sums, void* stream) {
+    ROWOP_CHECK(log_qz_prob && log_qz_prod && log_qz && lse_dim && pair_sums, "null pointer");
+    ROWOP_CHECK(b >= 1 && d >= 1 && dataset_size >= 1, "bad shape");
+    if (b < 2 && !(flags & TCELBO_EST_MWS)) return fail(TCELBO_ERR_INVALID, "b == 1: the stratified weight divides by B-1 (ops.py:44)");
+    Weights w; float lw_n, lw_s, post;
+    sampling_weights(b, dataset_size, flags, w, lw_n, lw_s, post);
+    cudaError_t e = launch_sampling_fwd(log_qz_prob, b, d, w, lw_n, lw_s, post, log_qz_prod, log_qz, lse_dim, pair_sums, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "sampling_fwd");
+}
+
+int tcelbo_sampling_backward(const float* log_qz_prob, int b, int d, int64_t dataset_size, uint32_t flags,
+                             const float* g_log_qz_prod, const float* g_log_qz, const float* lse_dim, const float* pair_sums,
+                             const float* log_qz, float* grad_log_qz_prob, void* stream) {
+    ROWOP_CHECK(log_qz_prob && g_log_qz_prod && g_log_qz && lse_dim && pair_sums && log_qz && grad_log_qz_prob, "null pointer");
+    Weights w; float lw_n, lw_s, post;
+    sampling_weights(b, dataset_size, flags, w, lw_n, lw_s, post);
+    cudaError_t e = launch_sampling_bwd(log_qz_prob, b, d, w, lw_n, lw_s, post, g_log_qz_prod, g_log_qz, lse_dim, pair_sums, log_qz,
+                                        grad_log_qz_prob, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "sampling_bwd");
 }
 
 long long tcelbo_launch_count(void) { return instr().launches.load(); }

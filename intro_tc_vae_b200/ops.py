@@ -25,7 +25,8 @@ from .sharding import gather_rows, shard_rows
 
 __all__ = [
     "total_correlation", "tc_terms", "kl_tc_loss_terms", "kl_divergence", "kl_no_reduce", "reparameterize",
-    "log_importance_weight_matrix", "row_log_density",
+    "log_importance_weight_matrix", "row_log_density", "gaussian_log_density_torch", "gaussian_log_density",
+    "minibatch_stratified_sampling", "minibatch_weighted_sampling",
 ]
 
 
@@ -448,6 +449,124 @@ def row_log_density(x: Tensor, mu: Optional[Tensor] = None, logvar: Optional[Ten
     if logvar is not None:
         _check("logvar", logvar)
     return _RowDensity.apply(x, mu, logvar)
+
+
+# --------------------------------------------------------------------------------------------------
+# materialised-tensor helpers of the reference's ops.py (API parity; HBM-bound, off the fused path)
+# --------------------------------------------------------------------------------------------------
+def _bcast3(*ts: Tensor):
+    """Broadcast to one shape of at most 3 dims; returns (views, shape3, element strides per operand)."""
+    for i, t in enumerate(ts):
+        if not isinstance(t, Tensor) or not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"operand {i} must be an fp32 CUDA tensor: the B200 path has no CPU fallback")
+    views = torch.broadcast_tensors(*ts)
+    shape = tuple(views[0].shape)
+    if len(shape) > 3:
+        raise NotImplementedError(f"at most 3 broadcast dims are supported, got shape {shape}")
+    pad = 3 - len(shape)
+    shape3 = (1,) * pad + shape
+    strides = [(0,) * pad + tuple(v.stride()) for v in views]
+    return views, shape, shape3, strides
+
+
+class _Density(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, mu: Tensor, logvar: Tensor, floored: bool) -> Tensor:
+        import ctypes
+        lib = _lib.load()
+        views, shape, shape3, strides = _bcast3(x, mu, logvar)
+        out = torch.empty(shape, dtype=torch.float32, device=x.device)
+        arr = lambda v: (ctypes.c_int64 * 3)(*v)
+        with torch.cuda.device(x.device):
+            st = lib.tcelbo_density_forward(int(floored), views[0].data_ptr(), views[1].data_ptr(), views[2].data_ptr(),
+                                            arr(shape3), arr(strides[0]), arr(strides[1]), arr(strides[2]), out.data_ptr(), _stream(x))
+        _lib.check(st, "tcelbo_density_forward")
+        ctx.save_for_backward(x, mu, logvar)
+        ctx.floored = floored
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        import ctypes
+        lib = _lib.load()
+        x, mu, logvar = ctx.saved_tensors
+        views, shape, shape3, strides = _bcast3(x, mu, logvar)
+        g = g.contiguous()
+        gx, gmu, glv = (torch.empty(shape, dtype=torch.float32, device=x.device) for _ in range(3))
+        arr = lambda v: (ctypes.c_int64 * 3)(*v)
+        with torch.cuda.device(x.device):
+            st = lib.tcelbo_density_backward(int(ctx.floored), views[0].data_ptr(), views[1].data_ptr(), views[2].data_ptr(),
+                                             g.data_ptr(), arr(shape3), arr(strides[0]), arr(strides[1]), arr(strides[2]),
+                                             gx.data_ptr(), gmu.data_ptr(), glv.data_ptr(), _stream(x))
+        _lib.check(st, "tcelbo_density_backward")
+        return gx.sum_to_size(x.shape), gmu.sum_to_size(mu.shape), glv.sum_to_size(logvar.shape), None
+
+
+def gaussian_log_density_torch(x: Tensor, mu: Tensor, logvar: Tensor) -> Tensor:
+    """ops.py:15-21: elementwise (broadcasting) Gaussian log-density with the 1e-4 variance floor
+    (straight-through gradient) and the -50 clamp.  Materialises the broadcast shape -- use :func:`tc_terms`
+    for the fused estimator."""
+    return _Density.apply(x, mu, logvar, True)
+
+
+def gaussian_log_density(x: Tensor, mu: Tensor, logvar: Tensor) -> Tensor:
+    """ops.py:24-29: un-floored variant, clamped at -50."""
+    return _Density.apply(x, mu, logvar, False)
+
+
+class _Sampling(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_qz_prob: Tensor, dataset_size: int, flags: int):
+        lib = _lib.load()
+        lp = log_qz_prob.contiguous()
+        b, d = lp.shape[0], lp.shape[2]
+        dev = lp.device
+        prod = torch.empty(b, dtype=torch.float32, device=dev)
+        joint = torch.empty(b, dtype=torch.float32, device=dev)
+        lse_d = torch.empty(b, d, dtype=torch.float32, device=dev)
+        srow = torch.empty(b, b, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.tcelbo_sampling_forward(lp.data_ptr(), b, d, dataset_size, flags, prod.data_ptr(), joint.data_ptr(),
+                                             lse_d.data_ptr(), srow.data_ptr(), _stream(lp))
+        _lib.check(st, "tcelbo_sampling_forward")
+        ctx.save_for_backward(lp, lse_d, srow, joint)
+        ctx.meta = (dataset_size, flags)
+        return prod, joint
+
+    @staticmethod
+    def backward(ctx, g_prod, g_joint):
+        lib = _lib.load()
+        lp, lse_d, srow, joint = ctx.saved_tensors
+        dataset_size, flags = ctx.meta
+        b, d = lp.shape[0], lp.shape[2]
+        g_prod = torch.zeros_like(joint) if g_prod is None else g_prod.contiguous()
+        g_joint = torch.zeros_like(joint) if g_joint is None else g_joint.contiguous()
+        glp = torch.empty_like(lp)
+        with torch.cuda.device(lp.device):
+            st = lib.tcelbo_sampling_backward(lp.data_ptr(), b, d, dataset_size, flags, g_prod.data_ptr(), g_joint.data_ptr(),
+                                              lse_d.data_ptr(), srow.data_ptr(), joint.data_ptr(), glp.data_ptr(), _stream(lp))
+        _lib.check(st, "tcelbo_sampling_backward")
+        return glp, None, None
+
+
+def _sampling(log_qz_prob: Tensor, batch_size: int, dataset_size: int, flags: int):
+    if not isinstance(log_qz_prob, Tensor) or not log_qz_prob.is_cuda or log_qz_prob.dtype != torch.float32:
+        raise RuntimeError("log_qz_prob must be an fp32 CUDA tensor: the B200 path has no CPU fallback")
+    if log_qz_prob.dim() != 3 or log_qz_prob.shape[0] != batch_size or log_qz_prob.shape[1] != batch_size:
+        raise ValueError(f"log_qz_prob must be [batch, batch, latent] with batch={batch_size}, got {tuple(log_qz_prob.shape)}")
+    if batch_size == 1 and flags == _lib.EST_MSS:
+        raise ZeroDivisionError("float division by zero")
+    return _Sampling.apply(log_qz_prob, int(dataset_size), flags)
+
+
+def minibatch_stratified_sampling(log_qz_prob: Tensor, batch_size: int, dataset_size: int):
+    """ops.py:104-115 on a materialised [B,B,D] tensor: (sum_d LSE_j(logW + lp), LSE_j(logW + sum_d lp))."""
+    return _sampling(log_qz_prob, batch_size, dataset_size, _lib.EST_MSS)
+
+
+def minibatch_weighted_sampling(log_qz_prob: Tensor, batch_size: int, dataset_size: int):
+    """ops.py:92-101 on a materialised [B,B,D] tensor."""
+    return _sampling(log_qz_prob, batch_size, dataset_size, _lib.EST_MWS)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -464,3 +464,33 @@ def test_solver_train_step_end_to_end(solver_name):
     prod_o, _ = O.tc_terms(z_c, mu_c, lv_c, 16704)
     assert abs(got.item() - want.item()) < LOSS_RTOL * prod_o.abs().mean().item()
     assert relerr(per, want_per) < LOSS_RTOL * max(1.0, 512.0 * prod_o.abs().max().item() / want_per.abs().max().item())
+
+
+@pytest.mark.parametrize("name", ["base_B64_D128", "stress_B64_D128", "ragged_B37_D20", "pair_B2_D16"])
+def test_materialised_helpers_match_reference(golden, name):
+    """ops.py's stand-alone helpers (API parity): densities on broadcast operands + the two estimators on the
+    materialised [B,B,D] tensor reproduce the fused results / the reference, values and gradients."""
+    ops = _ops()
+    case = CASES[name]
+    B, N, beta = case["B"], case["N"], case["beta"]
+    pre = f"{name}/f32/"
+    mu, lv, eps, _ = _cuda_leafs(case)
+    z = ops.reparameterize(mu, lv, eps)
+    lp = ops.gaussian_log_density_torch(z.unsqueeze(1), mu.unsqueeze(0), lv.unsqueeze(1))       # ops.py:80-82
+    assert lp.shape == (B, B, case["D"])
+    prod, joint = ops.minibatch_stratified_sampling(lp, B, N)
+    assert relerr(prod, golden[pre + "log_qz_prod"]) < LOSS_RTOL
+    assert relerr(joint, golden[pre + "log_qz"]) < LOSS_RTOL
+    prod_w, joint_w = ops.minibatch_weighted_sampling(lp, B, N)
+    assert relerr(prod_w, golden[pre + "mws_log_qz_prod"]) < LOSS_RTOL
+    assert relerr(joint_w, golden[pre + "mws_log_qz"]) < LOSS_RTOL
+    loss = (beta - 1.0) * (joint - prod).mean() + ops.kl_divergence(lv, mu, reduce="mean")
+    loss.backward()
+    assert relerr(mu.grad, golden[pre + "simple_mean_dmu"]) < GRAD_RTOL
+    assert relerr(lv.grad, golden[pre + "simple_mean_dlv"]) < GRAD_RTOL
+    lpj = ops.gaussian_log_density(z.detach().unsqueeze(1), mu.detach().unsqueeze(0), lv.detach().unsqueeze(0))   # solvers/tc.py:114-116
+    prod_j, joint_j = ops.minibatch_stratified_sampling(lpj, B, N)
+    assert relerr(prod_j, golden[pre + "varj_log_qz_prod"]) < LOSS_RTOL
+    assert relerr(joint_j, golden[pre + "varj_log_qz"]) < LOSS_RTOL
+    row = ops.gaussian_log_density(z.detach(), mu.detach(), lv.detach()).sum(1)                  # same-shape (row-wise) use
+    assert relerr(row, ops.row_log_density(z.detach(), mu.detach(), lv.detach())) < 1e-6
