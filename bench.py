@@ -354,9 +354,22 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None                                         # dram bytes per launch of the dominant kernel, from the committed ncu capture
+        try:
+            import csv
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_final_raw.csv"))))
+            hdr, units = rows[0], rows[1]
+            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for r in rows[2:]:
+                if dom.replace("_kernel", "") in r[ik]:
+                    traffic = float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
+        except Exception:
+            traffic = None
         roof = {
             "bound": "sfu", "kernel": dom, "achieved": achieved / 1e9, "peak": peak_nominal / 1e9, "unit": "Gex2/s",
-            "frac": achieved / peak_nominal, "traffic": None,
+            "frac": achieved / peak_nominal, "traffic": traffic,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel (bytes, profiles/r1_ncu_full_final_raw.csv, N=1 shape)",
             "peak_note": "148 SM x 16 MUFU/clk x 1.965 GHz (max SM clock); ex2_measured_gps is the in-job saturation probe",
             "ex2_measured_gps": ex2_measured / 1e9, "frac_of_measured_ex2": achieved / ex2_measured,
             "peak_at_observed_clock_gps": peak_at_clock / 1e9,
