@@ -396,7 +396,6 @@ int tcelbo_profile_events(int kernel_id, void* start_event, void* stop_event) {
 
 int tcelbo_set_tuning(const char* key, int value) {
     if (key && std::strcmp(key, "bwd_variant") == 0) { set_bwd_variant(value); return TCELBO_OK; }
-    if (key && std::strcmp(key, "fwd_variant") == 0) { set_fwd_variant(value); return TCELBO_OK; }
     return fail(TCELBO_ERR_INVALID, "unknown tuning key");
 }
 

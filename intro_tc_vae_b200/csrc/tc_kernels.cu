@@ -228,166 +228,6 @@ tc_fwd_kernel(const FwdArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------------
-// Forward sweep, two rows per thread (D = 128): 8 lanes share a PAIR of adjacent rows, each lane owns 16 dims of both
-// (16-byte chunks {l + 8k}, k = 0..3).  A column's mu chunk is loaded once and used for both rows, which halves the
-// LDS.128 count per log-density (the LPR = 4 kernel's top stall is mio_throttle), and the 8 d-sums of 4 columns x 2 rows
-// are reduced by a transposed butterfly: 7 shuffles leave each of the 8 lanes with one finished pair (row, column).
-// ------------------------------------------------------------------------------------------------------
-template <bool kWeighted>
-__device__ __forceinline__ void fwd2_one_column(const float* __restrict__ mu_row,           // smem row of column j, + 4*l
-                                                const u64 (&z2)[2][8], const u64 (&n2)[2][8], const float (&qmx)[2][16],
-                                                u64 (&S2)[2][8], float rho0, float rho1, float& part0, float& part1) {
-    u64 acc[2] = {0ull, 0ull};
-    const u64 rho2[2] = {pack2(rho0, rho0), pack2(rho1, rho1)};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float4 m = *reinterpret_cast<const float4*>(mu_row + 32 * k);
-        const u64 m01 = pack2(m.x, m.y), m23 = pack2(m.z, m.w);
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const u64 d01 = ffma2(m01, n2[r][2 * k], z2[r][2 * k]);
-            const u64 d23 = ffma2(m23, n2[r][2 * k + 1], z2[r][2 * k + 1]);
-            const u64 q01 = fmul2(d01, d01);
-            const u64 q23 = fmul2(d23, d23);
-            float q0, q1, q2_, q3;
-            unpack2(q01, q0, q1); unpack2(q23, q2_, q3);
-            q0 = fmin_nan(q0, qmx[r][4 * k + 0]); q1 = fmin_nan(q1, qmx[r][4 * k + 1]);
-            q2_ = fmin_nan(q2_, qmx[r][4 * k + 2]); q3 = fmin_nan(q3, qmx[r][4 * k + 3]);
-            u64 e01 = pack2(ex2(-q0), ex2(-q1));
-            u64 e23 = pack2(ex2(-q2_), ex2(-q3));
-            if (kWeighted) { e01 = fmul2(e01, rho2[r]); e23 = fmul2(e23, rho2[r]); }
-            S2[r][2 * k] = fadd2(S2[r][2 * k], e01);
-            S2[r][2 * k + 1] = fadd2(S2[r][2 * k + 1], e23);
-            acc[r] = fadd2(acc[r], fadd2(pack2(q0, q1), pack2(q2_, q3)));
-        }
-    }
-    float a, b;
-    unpack2(acc[0], a, b); part0 = a + b;
-    unpack2(acc[1], a, b); part1 = a + b;
-}
-
-template <bool kSpecial>
-__device__ __forceinline__ void fwd2_tile(const float* __restrict__ tile, int jt, int jt0, int l, int i_glob0,
-                                          const Weights& w, const u64 (&z2)[2][8], const u64 (&n2)[2][8], const float (&qmx)[2][16],
-                                          u64 (&S2)[2][8], float& lse_m, float& lse_s, float* __restrict__ s2_row_mine) {
-    const bool b4 = (l & 4) != 0, b2 = (l & 2) != 0, b1 = (l & 1) != 0;
-    const int my_r = l >> 2, my_u = l & 3;                                   // the (row, column) pair this lane finishes
-    for (int jj = 0; jj < jt; jj += 4) {
-        float v[8];                                                          // index r * 4 + u
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float rho0 = 1.0f, rho1 = 1.0f, l2;
-            if (kSpecial) { weight_of(w, i_glob0, jt0 + jj + u, rho0, l2); weight_of(w, i_glob0 + 1, jt0 + jj + u, rho1, l2); }
-            fwd2_one_column<kSpecial>(tile + (jj + u) * 128 + 4 * l, z2, n2, qmx, S2, rho0, rho1, v[u], v[4 + u]);
-        }
-        float wv[4], xv[2];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float send = b4 ? v[k] : v[k + 4], keep = b4 ? v[k + 4] : v[k];
-            wv[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float send = b2 ? wv[k] : wv[k + 2], keep = b2 ? wv[k + 2] : wv[k];
-            xv[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-        const float send = b1 ? xv[0] : xv[1], keep = b1 ? xv[1] : xv[0];
-        const float mine = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        const int j = jt0 + jj + my_u;
-        float x = -mine;
-        if (kSpecial) { float rho, l2; weight_of(w, i_glob0 + my_r, j, rho, l2); x += l2; }
-        lse2_push(lse_m, lse_s, x);
-        if (s2_row_mine != nullptr) s2_row_mine[j] = mine;
-    }
-}
-
-__global__ void __launch_bounds__(kFwdWarps * 32, 3)
-tc_fwd_r2_kernel(const FwdArgs a) {
-    constexpr int DP = 128, LPR = 8, JT = 32, TILE = JT * DP, ROWS = kFwdWarps * 8;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* tiles = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * TILE * sizeof(float));
-    uint64_t* bar_empty = bar_full + kStages;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int l = lane % LPR, grp = lane / LPR;
-    const int row0 = blockIdx.x * ROWS + warp * 8 + 2 * grp;                 // this thread's rows: row0, row0 + 1
-    const int i_glob0 = a.row_offset + row0;
-
-    u64 z2[2][8], n2[2][8], S2[2][8];
-    float qmx[2][16];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const float* pz = a.zs + (size_t)(row0 + r) * DP + 4 * l;
-        const float* pn = a.ns + (size_t)(row0 + r) * DP + 4 * l;
-        const float* pq = a.qmax + (size_t)(row0 + r) * DP + 4 * l;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float4 vz = __ldg(reinterpret_cast<const float4*>(pz + 32 * k));
-            const float4 vn = __ldg(reinterpret_cast<const float4*>(pn + 32 * k));
-            const float4 vq = __ldg(reinterpret_cast<const float4*>(pq + 32 * k));
-            z2[r][2 * k] = pack2(vz.x, vz.y); z2[r][2 * k + 1] = pack2(vz.z, vz.w);
-            n2[r][2 * k] = pack2(vn.x, vn.y); n2[r][2 * k + 1] = pack2(vn.z, vn.w);
-            qmx[r][4 * k] = vq.x; qmx[r][4 * k + 1] = vq.y; qmx[r][4 * k + 2] = vq.z; qmx[r][4 * k + 3] = vq.w;
-            S2[r][2 * k] = 0ull; S2[r][2 * k + 1] = 0ull;
-        }
-    }
-    float lse_m = kNegBig, lse_s = 0.0f;
-    const int j0 = blockIdx.y * a.js_len;
-    const int j1 = min(a.bg_pad, j0 + a.js_len);
-    const int ntiles = (j1 - j0) / JT;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kFwdWarps); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && ntiles > 0) {
-        mbar_arrive_expect_tx(&bar_full[0], TILE * sizeof(float));
-        bulk_g2s(tiles, a.mu_pad + (size_t)j0 * DP, TILE * sizeof(float), &bar_full[0]);
-    }
-    float* s2_row_mine = (a.s2 != nullptr) ? a.s2 + (size_t)(row0 + (l >> 2)) * a.ld_s2 : nullptr;
-
-    for (int t = 0; t < ntiles; ++t) {
-        const int st = t % kStages;
-        if (threadIdx.x == 0 && t + 1 < ntiles) {
-            const int sn = (t + 1) % kStages;
-            if (t + 1 >= kStages) mbar_wait(&bar_empty[sn], (((t + 1) / kStages) - 1) & 1);
-            mbar_arrive_expect_tx(&bar_full[sn], TILE * sizeof(float));
-            bulk_g2s(tiles + (size_t)sn * TILE, a.mu_pad + (size_t)(j0 + (t + 1) * JT) * DP, TILE * sizeof(float), &bar_full[sn]);
-        }
-        mbar_wait(&bar_full[st], (t / kStages) & 1);
-        const float* tile = tiles + (size_t)st * TILE;
-        const int jt0 = j0 + t * JT;
-        const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
-        if (special) fwd2_tile<true>(tile, JT, jt0, l, i_glob0, a.w, z2, n2, qmx, S2, lse_m, lse_s, s2_row_mine);
-        else         fwd2_tile<false>(tile, JT, jt0, l, i_glob0, a.w, z2, n2, qmx, S2, lse_m, lse_s, s2_row_mine);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_empty[st]);
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        float* ps = a.Spart + ((size_t)blockIdx.y * a.bl_pad + row0 + r) * DP + 4 * l;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float4 v;
-            unpack2(S2[r][2 * k], v.x, v.y); unpack2(S2[r][2 * k + 1], v.z, v.w);
-            *reinterpret_cast<float4*>(ps + 32 * k) = v;
-        }
-    }
-#pragma unroll
-    for (int o = 1; o < 4; o <<= 1) {                                        // the 4 lanes that served the same row
-        const float m2 = __shfl_xor_sync(0xffffffffu, lse_m, o);
-        const float s2v = __shfl_xor_sync(0xffffffffu, lse_s, o);
-        lse2_merge(lse_m, lse_s, m2, s2v);
-    }
-    if ((l & 3) == 0) {
-        float2* pj = reinterpret_cast<float2*>(a.Jpart) + (size_t)blockIdx.y * a.bl_pad + row0 + (l >> 2);
-        *pj = make_float2(lse_m, lse_s);
-    }
-}
-
 // One warp per row: sum the column-split partials (float4 per lane, 8 independent loads in flight), take logs,
 // emit log_qz / log_qz_prod and, when asked, the fused KL and (beta-1)*TC + KL of solvers/tc.py:83-89.
 __global__ void fwd_finalize_kernel(const FinArgs a) {
@@ -531,24 +371,7 @@ cudaError_t launch_row_prep(const float* z, int64_t ldz, const float* logvar, in
     return cudaGetLastError();
 }
 
-static int g_fwd_variant = 0;        // tcelbo_set_tuning("fwd_variant", v): 1 = two-rows-per-thread kernel at D = 128
-void set_fwd_variant(int v) { g_fwd_variant = v; }
-
-static cudaError_t launch_fwd_r2(const Plan& p, const FwdArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)kStages * 32 * 128 * sizeof(float) + 2 * kStages * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_fwd_r2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    LaunchScope scope(kKernFwd, st);
-    tc_fwd_r2_kernel<<<dim3(p.n_rb_fwd, p.n_js_fwd), kFwdWarps * 32, smem, st>>>(a);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st) {
-    if (p.dpt == 4 && g_fwd_variant == 1) return launch_fwd_r2(p, a, st);
     switch (p.dpt) {
         case 1:  return launch_fwd_t<1>(p, a, st);
         case 2:  return launch_fwd_t<2>(p, a, st);

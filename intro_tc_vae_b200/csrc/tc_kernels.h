@@ -60,7 +60,6 @@ cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g
                             float beta, const float* S, float* gps, float* gj, float* gk, float* zero, size_t zero_n, cudaStream_t st);
 cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out, cudaStream_t st);
 void set_bwd_variant(int v);
-void set_fwd_variant(int v);
 // column-variance ("full" path) variant, tc_colvar.cu
 cudaError_t launch_colvar_prep(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* lv_all, int64_t ldlv,
                                const Plan& p, float* colpack, float* zpad, float* shift, cudaStream_t st);
