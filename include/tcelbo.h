@@ -154,6 +154,21 @@ int tcelbo_rowdensity_backward(const float* x, int64_t ldx, const float* mu, int
                                float* grad_logvar, int64_t ldglv, void* stream);
 
 /*
+ * Callers either side of the path:
+ *   per-sample reconstruction loss, ops.py:188-236: out_rows[i] = sum over the n pixels of sample i of
+ *     kind 0: (recon-x)^2   kind 1: |recon-x|   kind 2: binary cross entropy (logs clamped at -100);
+ *     x and recon are contiguous [b, n]; `partial` is scratch of b * tcelbo_recloss_chunks(b, n) floats;
+ *     the backward gives dLoss/drecon = g_rows[i] * d(elem)/d(recon) (x is detached in the reference).
+ *   soft-intro exp-ELBO term, solvers/intro.py:102-103: out[0] = mean_i exp(-2*scale*(rec_rows[i] + kl_rows[i]));
+ *     e_rows [b] is saved for the backward, which returns the common gradient of rec_rows and kl_rows.
+ */
+int tcelbo_recloss_chunks(int b, int64_t n);
+int tcelbo_recloss_forward(const float* x, const float* recon, int b, int64_t n, int kind, float* partial, float* out_rows, void* stream);
+int tcelbo_recloss_backward(const float* x, const float* recon, const float* g_rows, int b, int64_t n, int kind, float* grad_recon, void* stream);
+int tcelbo_expelbo_forward(const float* rec_rows, const float* kl_rows, int b, float scale, float* out, float* e_rows, void* stream);
+int tcelbo_expelbo_backward(const float* e_rows, const float* g_out, int b, float scale, float* g_rows, void* stream);
+
+/*
  * Materialised-tensor helpers kept for API parity with the reference's ops.py (HBM-bound; the fused ops above never
  * build the tensor).  Densities: out[i,j,d] over a broadcast 3-D index space, operand strides in elements (0 on
  * broadcast dims); floored != 0 selects gaussian_log_density_torch (ops.py:15-21), else gaussian_log_density

@@ -46,6 +46,11 @@ _SIGNATURES = {
     "tcelbo_rowdensity_forward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_void_p]),
     "tcelbo_rowdensity_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, _f, c_int, c_int,
                                            _f, c_int64, _f, c_int64, _f, c_int64, c_void_p]),
+    "tcelbo_recloss_chunks": (c_int, [c_int, c_int64]),
+    "tcelbo_recloss_forward": (c_int, [_f, _f, c_int, c_int64, c_int, _f, _f, c_void_p]),
+    "tcelbo_recloss_backward": (c_int, [_f, _f, _f, c_int, c_int64, c_int, _f, c_void_p]),
+    "tcelbo_expelbo_forward": (c_int, [_f, _f, c_int, c_float, _f, _f, c_void_p]),
+    "tcelbo_expelbo_backward": (c_int, [_f, _f, c_int, c_float, _f, c_void_p]),
     "tcelbo_density_forward": (c_int, [c_int, _f, _f, _f, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
                                        _f, c_void_p]),
     "tcelbo_density_backward": (c_int, [c_int, _f, _f, _f, _f, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),

@@ -335,6 +335,40 @@ int tcelbo_rowdensity_backward(const float* x, int64_t ldx, const float* mu, int
     return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "rowdensity_bwd");
 }
 
+int tcelbo_recloss_chunks(int b, int64_t n) {
+    int c = (int)((n + 4095) / 4096);                       // ~4K pixels per CTA, enough CTAs to fill the GPU at small batches
+    const int want = (148 * 4 + b - 1) / (b > 0 ? b : 1);
+    if (c > want) c = want;
+    if (c < 1) c = 1;
+    return c;
+}
+
+int tcelbo_recloss_forward(const float* x, const float* recon, int b, int64_t n, int kind, float* partial, float* out_rows, void* stream) {
+    ROWOP_CHECK(x && recon && partial && out_rows, "null pointer");
+    ROWOP_CHECK(b >= 1 && n >= 1 && kind >= 0 && kind <= 2, "bad argument");
+    cudaError_t e = launch_recloss_fwd(x, recon, b, n, kind, partial, tcelbo_recloss_chunks(b, n), out_rows, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "recloss_fwd");
+}
+
+int tcelbo_recloss_backward(const float* x, const float* recon, const float* g_rows, int b, int64_t n, int kind, float* grad_recon, void* stream) {
+    ROWOP_CHECK(x && recon && g_rows && grad_recon, "null pointer");
+    ROWOP_CHECK(b >= 1 && n >= 1 && kind >= 0 && kind <= 2, "bad argument");
+    cudaError_t e = launch_recloss_bwd(x, recon, g_rows, b, n, kind, grad_recon, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "recloss_bwd");
+}
+
+int tcelbo_expelbo_forward(const float* rec_rows, const float* kl_rows, int b, float scale, float* out, float* e_rows, void* stream) {
+    ROWOP_CHECK(rec_rows && kl_rows && out && e_rows && b >= 1, "bad argument");
+    cudaError_t e = launch_expelbo_fwd(rec_rows, kl_rows, b, scale, out, e_rows, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "expelbo_fwd");
+}
+
+int tcelbo_expelbo_backward(const float* e_rows, const float* g_out, int b, float scale, float* g_rows, void* stream) {
+    ROWOP_CHECK(e_rows && g_out && g_rows && b >= 1, "bad argument");
+    cudaError_t e = launch_expelbo_bwd(e_rows, g_out, b, scale, g_rows, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "expelbo_bwd");
+}
+
 int tcelbo_density_forward(int floored, const float* x, const float* mu, const float* logvar, const int64_t* shape,
                            const int64_t* sx, const int64_t* sm, const int64_t* sl, float* out, void* stream) {
     ROWOP_CHECK(x && mu && logvar && out && shape && sx && sm && sl, "null pointer");

@@ -102,6 +102,110 @@ __global__ void rowdensity_bwd_kernel(const float* __restrict__ x, int64_t ldx, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Per-sample reconstruction loss (ops.py:188-236): sum over the C*H*W pixels of mse / l1 / bce, x detached.
+// grid = (chunks, samples); each CTA reduces one chunk of one sample with float4 loads, a second tiny kernel adds
+// the chunk partials in a fixed order (deterministic).  kind: 0 = mse, 1 = l1, 2 = bce (log clamped at -100 as in
+// torch.nn.functional.binary_cross_entropy).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rec_elem(int kind, float x, float r) {
+    if (kind == 0) { const float t = r - x; return t * t; }
+    if (kind == 1) return fabsf(r - x);
+    return -(x * fmaxf(logf(r), -100.0f) + (1.0f - x) * fmaxf(logf(1.0f - r), -100.0f));
+}
+__device__ __forceinline__ float rec_grad(int kind, float x, float r) {
+    if (kind == 0) return 2.0f * (r - x);
+    if (kind == 1) return (r > x) ? 1.0f : ((r < x) ? -1.0f : 0.0f);
+    const float a = (logf(r) > -100.0f) ? -x / r : 0.0f;
+    const float b = (logf(1.0f - r) > -100.0f) ? (1.0f - x) / (1.0f - r) : 0.0f;
+    return a + b;
+}
+
+__global__ void recloss_partial_kernel(const float* __restrict__ x, const float* __restrict__ r, int64_t n, int kind,
+                                       float* __restrict__ partial /*[samples][chunks]*/) {
+    __shared__ float sh[8];
+    const int chunk = blockIdx.x, nchunk = gridDim.x, i = blockIdx.y;
+    const int64_t per = (n + nchunk - 1) / nchunk;
+    const int64_t lo = (int64_t)chunk * per, hi = (lo + per < n) ? lo + per : n;
+    const float* xs = x + (int64_t)i * n;
+    const float* rs = r + (int64_t)i * n;
+    float acc = 0.0f;
+    for (int64_t k = lo + threadIdx.x; k < hi; k += blockDim.x) acc += rec_elem(kind, xs[k], rs[k]);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];
+        partial[(int64_t)i * nchunk + chunk] = t;
+    }
+}
+
+__global__ void recloss_finish_kernel(const float* __restrict__ partial, int b, int nchunk, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    float t = 0.0f;
+    for (int c = 0; c < nchunk; ++c) t += partial[(int64_t)i * nchunk + c];
+    out[i] = t;
+}
+
+__global__ void recloss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ g_rows,
+                                   int64_t n, int64_t total, int kind, float* __restrict__ gr) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x)
+        gr[idx] = g_rows[idx / n] * rec_grad(kind, x[idx], r[idx]);
+}
+
+// Soft-intro exp-ELBO term (solvers/intro.py:102-103): out = mean_i exp(-2*scale*(rec_i + kl_i)); one CTA.
+__global__ void expelbo_fwd_kernel(const float* __restrict__ rec, const float* __restrict__ kl, int b, float scale,
+                                   float* __restrict__ out, float* __restrict__ e_rows) {
+    __shared__ float sh[8];
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+        const float e = expf(-2.0f * scale * (rec[i] + kl[i]));
+        e_rows[i] = e;
+        acc += e;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];
+        out[0] = t / (float)b;
+    }
+}
+
+__global__ void expelbo_bwd_kernel(const float* __restrict__ e_rows, const float* __restrict__ g, int b, float scale,
+                                   float* __restrict__ g_rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b) g_rows[i] = g[0] * (-2.0f * scale / (float)b) * e_rows[i];      // same gradient for rec_i and kl_i
+}
+
+cudaError_t launch_recloss_fwd(const float* x, const float* r, int b, int64_t n, int kind, float* partial, int nchunk, float* out, cudaStream_t st) {
+    { LaunchScope scope(kKernNone, st); recloss_partial_kernel<<<dim3(nchunk, b), 256, 0, st>>>(x, r, n, kind, partial); }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    { LaunchScope scope(kKernNone, st); recloss_finish_kernel<<<(b + 127) / 128, 128, 0, st>>>(partial, b, nchunk, out); }
+    return cudaGetLastError();
+}
+cudaError_t launch_recloss_bwd(const float* x, const float* r, const float* g_rows, int b, int64_t n, int kind, float* gr, cudaStream_t st) {
+    const int64_t total = (int64_t)b * n;
+    int64_t g = (total + 255) / 256; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1;
+    LaunchScope scope(kKernNone, st);
+    recloss_bwd_kernel<<<(int)g, 256, 0, st>>>(x, r, g_rows, n, total, kind, gr);
+    return cudaGetLastError();
+}
+cudaError_t launch_expelbo_fwd(const float* rec, const float* kl, int b, float scale, float* out, float* e_rows, cudaStream_t st) {
+    LaunchScope scope(kKernNone, st);
+    expelbo_fwd_kernel<<<1, 256, 0, st>>>(rec, kl, b, scale, out, e_rows);
+    return cudaGetLastError();
+}
+cudaError_t launch_expelbo_bwd(const float* e_rows, const float* g, int b, float scale, float* g_rows, cudaStream_t st) {
+    LaunchScope scope(kKernNone, st);
+    expelbo_bwd_kernel<<<(b + 255) / 256, 256, 0, st>>>(e_rows, g, b, scale, g_rows);
+    return cudaGetLastError();
+}
+
 // MUFU.EX2 saturation probe: 8 independent dependency chains per thread, nothing but ex2 in the loop.
 __global__ void __launch_bounds__(256) ex2_peak_kernel(float* __restrict__ out, int iters) {
     float v[8];

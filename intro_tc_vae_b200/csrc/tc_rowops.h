@@ -15,5 +15,9 @@ cudaError_t launch_rowdensity_fwd(const float* x, int64_t ldx, const float* mu, 
 cudaError_t launch_rowdensity_bwd(const float* x, int64_t ldx, const float* mu, int64_t ldmu, const float* lv, int64_t ldlv,
                                   const float* g_rows, int b, int d, float* gx, int64_t ldgx, float* gmu, int64_t ldgmu,
                                   float* glv, int64_t ldglv, cudaStream_t st);
+cudaError_t launch_recloss_fwd(const float* x, const float* r, int b, int64_t n, int kind, float* partial, int nchunk, float* out, cudaStream_t st);
+cudaError_t launch_recloss_bwd(const float* x, const float* r, const float* g_rows, int b, int64_t n, int kind, float* gr, cudaStream_t st);
+cudaError_t launch_expelbo_fwd(const float* rec, const float* kl, int b, float scale, float* out, float* e_rows, cudaStream_t st);
+cudaError_t launch_expelbo_bwd(const float* e_rows, const float* g, int b, float scale, float* g_rows, cudaStream_t st);
 cudaError_t launch_ex2_peak(float* out, int iters, int ctas, cudaStream_t st);
 }  // namespace tcelbo

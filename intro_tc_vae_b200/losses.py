@@ -1,32 +1,104 @@
-"""Reconstruction loss with the reference's signature (reference ``ops.py:188-236``).
-
-Adjacent to the TC path: a streaming per-sample reduction over C*H*W pixels that
-feeds the exp-ELBO terms.  Runs as torch ops on the caller's device for now.
-"""
+"""Callers either side of the TC path: the per-sample reconstruction loss (reference
+``ops.py:188-236``) and the soft-intro exp-ELBO term (``solvers/intro.py:102-103``), as CUDA kernels behind
+the reference's signatures.  fp32 CUDA tensors only (no CPU fallback)."""
 from __future__ import annotations
 
-import torch.nn.functional as F
+import torch
 from torch import Tensor
+
+from . import _lib
+
+_KINDS = {"mse": 0, "l1": 1, "bce": 2}
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _RecRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, recon: Tensor, kind: int) -> Tensor:
+        lib = _lib.load()
+        b, n = recon.shape
+        out = torch.empty(b, dtype=torch.float32, device=recon.device)
+        partial = torch.empty(b * lib.tcelbo_recloss_chunks(b, n), dtype=torch.float32, device=recon.device)
+        with torch.cuda.device(recon.device):
+            st = lib.tcelbo_recloss_forward(x.data_ptr(), recon.data_ptr(), b, n, kind, partial.data_ptr(), out.data_ptr(), _stream(recon))
+        _lib.check(st, "tcelbo_recloss_forward")
+        ctx.save_for_backward(x, recon)
+        ctx.kind = kind
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        lib = _lib.load()
+        x, recon = ctx.saved_tensors
+        b, n = recon.shape
+        g = g.contiguous()
+        gr = torch.empty_like(recon)
+        with torch.cuda.device(recon.device):
+            st = lib.tcelbo_recloss_backward(x.data_ptr(), recon.data_ptr(), g.data_ptr(), b, n, ctx.kind, gr.data_ptr(), _stream(recon))
+        _lib.check(st, "tcelbo_recloss_backward")
+        return None, gr, None
 
 
 def reconstruction_loss(x: Tensor, recon_x: Tensor, loss_type: str = "mse", reduction: str = "sum") -> Tensor:
+    """ops.py:188-236: per-sample sum over pixels of mse / l1 / bce, then ``reduction`` in {"sum", "mean", "none"}
+    over the batch.  ``x`` is treated as a constant (the reference detaches it)."""
     if x.size(0) == 0:
         raise AssertionError("empty batch")
     if reduction not in ("sum", "mean", "none"):
         raise NotImplementedError(reduction)
-    recon_x = recon_x.reshape(recon_x.size(0), -1)
-    x = x.reshape(x.size(0), -1).detach()
-    if loss_type == "mse":
-        err = F.mse_loss(recon_x, x, reduction="none")
-    elif loss_type == "l1":
-        err = F.l1_loss(recon_x, x, reduction="none")
-    elif loss_type == "bce":
-        err = F.binary_cross_entropy(recon_x, x, reduction="none")
-    else:
+    if loss_type not in _KINDS:
         raise NotImplementedError(loss_type)
-    err = err.sum(1)
+    for name, t in (("x", x), ("recon_x", recon_x)):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"{name} must be an fp32 CUDA tensor: the B200 path has no CPU fallback")
+    recon = recon_x.reshape(recon_x.size(0), -1).contiguous()
+    xf = x.reshape(x.size(0), -1).detach().contiguous()
+    if xf.shape != recon.shape:
+        raise ValueError(f"x and recon_x must have the same number of elements per sample, got {tuple(xf.shape)} and {tuple(recon.shape)}")
+    rows = _RecRows.apply(xf, recon, _KINDS[loss_type])
     if reduction == "sum":
-        return err.sum()
+        return rows.sum()
     if reduction == "mean":
-        return err.mean()
-    return err
+        return rows.mean()
+    return rows
+
+
+class _ExpElbo(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rec_rows: Tensor, kl_rows: Tensor, scale: float) -> Tensor:
+        lib = _lib.load()
+        rec_rows, kl_rows = rec_rows.contiguous(), kl_rows.contiguous()
+        b = rec_rows.shape[0]
+        out = torch.empty(1, dtype=torch.float32, device=rec_rows.device)
+        e_rows = torch.empty(b, dtype=torch.float32, device=rec_rows.device)
+        with torch.cuda.device(rec_rows.device):
+            st = lib.tcelbo_expelbo_forward(rec_rows.data_ptr(), kl_rows.data_ptr(), b, scale, out.data_ptr(), e_rows.data_ptr(), _stream(rec_rows))
+        _lib.check(st, "tcelbo_expelbo_forward")
+        ctx.save_for_backward(e_rows)
+        ctx.scale = scale
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        lib = _lib.load()
+        (e_rows,) = ctx.saved_tensors
+        b = e_rows.shape[0]
+        g = g.reshape(1).contiguous()
+        g_rows = torch.empty_like(e_rows)
+        with torch.cuda.device(e_rows.device):
+            st = lib.tcelbo_expelbo_backward(e_rows.data_ptr(), g.data_ptr(), b, ctx.scale, g_rows.data_ptr(), _stream(e_rows))
+        _lib.check(st, "tcelbo_expelbo_backward")
+        return g_rows, g_rows, None
+
+
+def exp_elbo(rec_per_sample: Tensor, kl_per_sample: Tensor, scale: float) -> Tensor:
+    """solvers/intro.py:102-103: ``(-2 * scale * (rec_i + kl_i)).exp().mean()`` as one kernel each way."""
+    if rec_per_sample.shape != kl_per_sample.shape or rec_per_sample.dim() != 1:
+        raise ValueError("rec_per_sample and kl_per_sample must be [B] vectors of one shape")
+    for name, t in (("rec_per_sample", rec_per_sample), ("kl_per_sample", kl_per_sample)):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"{name} must be an fp32 CUDA tensor: the B200 path has no CPU fallback")
+    return _ExpElbo.apply(rec_per_sample, kl_per_sample, float(scale))

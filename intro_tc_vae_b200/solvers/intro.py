@@ -12,6 +12,7 @@ import torch
 from torch import Tensor
 
 from .. import ops
+from ..losses import exp_elbo
 from .vae import VAESolver
 
 
@@ -37,7 +38,7 @@ class IntroSolver(VAESolver):
 
     def exp_elbo(self, rec_per_sample: Tensor, kl_per_sample: Tensor) -> Tensor:
         """solvers/intro.py:102-103."""
-        return (-2 * self.scale * (rec_per_sample + kl_per_sample)).exp().mean()
+        return exp_elbo(rec_per_sample, kl_per_sample, self.scale)
 
     def train_step(self, batch: Tensor, cur_iter: int) -> dict:
         if batch.dim() == 3:

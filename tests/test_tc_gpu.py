@@ -494,3 +494,53 @@ def test_materialised_helpers_match_reference(golden, name):
     assert relerr(joint_j, golden[pre + "varj_log_qz"]) < LOSS_RTOL
     row = ops.gaussian_log_density(z.detach(), mu.detach(), lv.detach()).sum(1)                  # same-shape (row-wise) use
     assert relerr(row, ops.row_log_density(z.detach(), mu.detach(), lv.detach())) < 1e-6
+
+
+def test_reconstruction_loss_reference_values():
+    """The reference's own unit tests for this function (tests/test_ops.py:10-45), on CUDA tensors."""
+    from intro_tc_vae_b200.losses import reconstruction_loss
+    x = torch.tensor([0.0, 0.0, 0.0], device="cuda:0")
+    r = torch.tensor([1.0, 2.0, 4.0], device="cuda:0")
+    assert reconstruction_loss(x, r, loss_type="mse", reduction="sum").item() == 21
+    assert reconstruction_loss(x, r, loss_type="mse", reduction="mean").item() == 7
+    none = reconstruction_loss(x, r, loss_type="mse", reduction="none")
+    assert none.dim() == 1 and none.tolist() == [1, 4, 16]
+    assert reconstruction_loss(x, r, loss_type="l1", reduction="sum").item() == 7
+    assert reconstruction_loss(x, r, loss_type="l1", reduction="mean").item() == pytest.approx(7 / 3)
+    assert reconstruction_loss(x, r, loss_type="l1", reduction="none").tolist() == [1, 2, 4]
+    with pytest.raises(NotImplementedError):
+        reconstruction_loss(x, r, loss_type="huber")
+    with pytest.raises(NotImplementedError):
+        reconstruction_loss(x, r, reduction="max")
+
+
+@pytest.mark.parametrize("loss_type", ["mse", "l1", "bce"])
+@pytest.mark.parametrize("shape", [(64, 3, 64, 64), (5, 1, 28, 28), (3, 7)])
+def test_reconstruction_loss_and_exp_elbo_against_torch(loss_type, shape):
+    import torch.nn.functional as F
+    from intro_tc_vae_b200.losses import reconstruction_loss, exp_elbo
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(shape, generator=g).cuda()
+    r0 = (torch.rand(shape, generator=g) * 0.98 + 0.01).cuda()
+    kl = (torch.randn(shape[0], generator=g) * 50 + 100).cuda()
+    scale = 1.0 / (3 * 64 * 64)
+    outs = []
+    for ours in (False, True):
+        r = r0.clone().requires_grad_(True)
+        k = kl.clone().requires_grad_(True)
+        if ours:
+            rows = reconstruction_loss(x, r, loss_type, "none")
+            tot = reconstruction_loss(x, r, loss_type, "mean")
+            ee = exp_elbo(rows, k, scale)
+        else:
+            fn = {"mse": F.mse_loss, "l1": F.l1_loss, "bce": F.binary_cross_entropy}[loss_type]
+            rows = fn(r.view(shape[0], -1), x.view(shape[0], -1), reduction="none").sum(1)
+            tot = rows.mean()
+            ee = (-2 * scale * (rows + k)).exp().mean()
+        (tot + 1000.0 * ee).backward()
+        outs.append((rows.detach(), tot.detach(), ee.detach(), r.grad, k.grad))
+    assert relerr(outs[1][0], outs[0][0]) < LOSS_RTOL
+    assert relerr(outs[1][1], outs[0][1]) < LOSS_RTOL
+    assert relerr(outs[1][2], outs[0][2]) < LOSS_RTOL
+    assert relerr(outs[1][3], outs[0][3]) < GRAD_RTOL
+    assert relerr(outs[1][4], outs[0][4]) < GRAD_RTOL
