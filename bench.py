@@ -212,10 +212,12 @@ def run_ours(args):
     barrier()
     graphed = None
     graph_note = "eager"
+    exchange_note = "nccl" if world > 1 else "none"
     if not args.no_graph:
         try:
             from intro_tc_vae_b200.graphs import GraphedKLLoss
-            graphed = GraphedKLLoss(b_loc, D, N, BETA, dev, group=group)
+            graphed = GraphedKLLoss(b_loc, D, N, BETA, dev, group=group, exchange=args.exchange)
+            exchange_note = graphed.exchange_kind
             graphed(mu.detach(), lv.detach(), eps)
             torch.cuda.synchronize()
             ref_loss = step(mu, lv, eps).item()
@@ -230,6 +232,8 @@ def run_ours(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if ok.item() == 0:
         graphed = None
+    if graphed is None:
+        exchange_note = "nccl" if world > 1 else "none"
 
     def run_step():
         if graphed is not None:
@@ -400,7 +404,9 @@ def run_ours(args):
                                    "MSS estimator, row-variance density, fwd+bwd",
                        "global_batch": B, "z_dim": D, "rows_per_gpu": b_loc, "parallelism": f"row-shard x{world}",
                        "l2": "flushed between timed steps by writing a 256 MiB buffer (outside the event pairs)",
-                       "launch": graph_note},
+                       "launch": graph_note,
+                       "exchange": {"none": "none (one GPU)", "nccl": "NCCL all-gather + reduce-scatter",
+                                    "peer": "library kernels over NVLink peer memory (symmetric memory + 2 barriers)"}[exchange_note]},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 3 * b_loc * D * 4, "d2h_bytes_per_step": 2 * b_loc * D * 4 + 4},
             "gpu_launches": int(launches),
@@ -430,6 +436,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="GLOBAL batch (rows are sharded over the ranks)")
     ap.add_argument("--zdim", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1: how the column operand / its gradient cross ranks (peer memory inside the kernels, or NCCL)")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

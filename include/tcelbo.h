@@ -125,6 +125,36 @@ int tcelbo_klloss_backward(const float* z, int64_t ldz, const float* mu_all, int
                            float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
                            const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream);
 
+/*
+ * Peer-memory exchange for the row-sharded fused loss (one process per GPU).  Replaces the NCCL all-gather of
+ * the column operand and the reduce-scatter of its gradient (what a torch DistributedDataParallel port of solvers/tc.py:69-89
+ * would issue around ops.py:52-89) by loads over NVLink inside the library's own prep / finalize kernels:
+ *   forward : every rank publishes its [b_loc, d] rows of mu in a buffer that is mapped into all n_ranks processes (torch
+ *             symmetric memory, cudaIpc, a VMM fabric handle ...); after a cross-rank barrier ON THE STREAM (the caller's), the
+ *             column-prep kernel gathers the rows of all ranks through `mu_parts`, a DEVICE array of n_ranks pointers
+ *             (entry p = rank p's rows, row pitch ld_part floats).  b_glob = n_ranks * b_loc, row_offset = rank * b_loc.
+ *   backward: `scratch` must itself live in such a mapped buffer.  TCELBO_PEER_SWEEP runs the gradient sweep and leaves the
+ *             column sums in this rank's scratch; after another barrier, TCELBO_PEER_FINISH sums this rank's rows over the
+ *             scratch buffers of all ranks (`scratch_parts`, DEVICE array of n_ranks scratch base pointers) and writes
+ *             grad_z, grad_logvar and grad_mu_loc [b_loc, d] (the already reduce-scattered gradient of mu, KL term included).
+ * A scratch (and a published mu buffer) may be reused two exchanges later (double-buffer them), never by the very next one.
+ * `mu_loc` is this rank's rows of mu (the KL term reads it).  Row-variance density only.
+ */
+#define TCELBO_PEER_SWEEP  1
+#define TCELBO_PEER_FINISH 2
+int tcelbo_klloss_forward_peer(const float* z, int64_t ldz, const float* mu_loc, int64_t ldmu,
+                               const float* const* mu_parts, int64_t ld_part, const float* logvar, int64_t ldlv,
+                               int b_loc, int n_ranks, int rank, int d, int64_t dataset_size, uint32_t flags, float beta,
+                               float* loss_rows, float* kl_rows, float* log_qz, float* log_qz_prod,
+                               void* workspace, size_t workspace_bytes, void* stream);
+int tcelbo_klloss_backward_peer(int phase, const float* z, int64_t ldz, const float* mu_loc, int64_t ldmu,
+                                const float* logvar, int64_t ldlv, int b_loc, int n_ranks, int rank, int d,
+                                int64_t dataset_size, uint32_t flags, float beta,
+                                const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
+                                float* grad_z, int64_t ldgz, float* grad_mu_loc, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
+                                const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                                const void* const* scratch_parts, void* stream);
+
 /* kl_rows[i] = -0.5 * sum_d (1 + logvar - exp(logvar) - mu^2)   (ops.py:161-163; argument order logvar, mu) */
 int tcelbo_kl_forward(const float* logvar, int64_t ldlv, const float* mu, int64_t ldmu,
                       int b, int d, float* kl_rows, void* stream);

@@ -120,12 +120,23 @@ struct LossFusion {            // solvers/tc.py:83-89 folded into the finalize k
     bool on = false;
 };
 
+// Peer-memory exchange (tcelbo_*_peer): the column operand / the column accumulators live in n_ranks allocations that
+// are all mapped into this process (NVLink peer memory); in that mode `mu_all` is this rank's rows only.
+struct Peers {
+    const float* const* mu_parts = nullptr; int64_t ld_part = 0;   // forward: device table of every rank's [b_loc, d] rows of mu
+    const void* const* scratch_parts = nullptr;                    // backward finish: device table of every rank's scratch base
+    int n_ranks = 0;
+    int phase = 3;                                                 // backward: 1 = sweep into scratch, 2 = finish from the peers' scratch
+    bool on() const { return n_ranks > 0; }
+};
+
 static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
                         int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
                         float* log_qz, float* log_qz_prod, const LossFusion& lf,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+                        void* workspace, size_t workspace_bytes, void* stream, const Peers& peers = Peers()) {
     if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv)) return rc;
     if (!log_qz || !log_qz_prod) return fail(TCELBO_ERR_INVALID, "null output pointer");
+    if (peers.on() && (flags & TCELBO_VAR_COL)) return fail(TCELBO_ERR_UNSUPPORTED, "the peer-memory exchange covers the row-variance density");
     Plan p;
     if (!make_plan(p, b_loc, b_glob, d, flags, sm_count())) return fail(TCELBO_ERR_INVALID, "cannot plan this shape");
     if (!workspace || workspace_bytes < p.total_bytes || !aligned256(workspace))
@@ -147,7 +158,9 @@ static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_
     if (p.var_col) {
         if ((e = launch_colvar_prep(z, ldz, mu_all, ldmu, logvar, ldlv, p, mu_pad, zs, shift, st)) != cudaSuccess) return fail_cuda(e, "colvar_prep");
     } else {
-        if ((e = launch_col_prep(mu_all, ldmu, p, mu_pad, st)) != cudaSuccess) return fail_cuda(e, "col_prep");
+        if (peers.on()) {
+            if ((e = launch_col_prep_parts(peers.mu_parts, peers.ld_part, b_loc, p, mu_pad, st)) != cudaSuccess) return fail_cuda(e, "col_prep_parts");
+        } else if ((e = launch_col_prep(mu_all, ldmu, p, mu_pad, st)) != cudaSuccess) return fail_cuda(e, "col_prep");
         if ((e = launch_row_prep(z, ldz, logvar, ldlv, p, zs, ns, qmax, shift, vr, st)) != cudaSuccess) return fail_cuda(e, "row_prep");
     }
 
@@ -171,7 +184,7 @@ static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_
     fin.b_loc = b_loc; fin.bl_pad = p.bl_pad; fin.d = d; fin.dp = p.dp; fin.n_js = n_js_used; fin.lw_u = w.lw_u;
     fin.lv = nullptr; fin.ldlv = 0; fin.mu_loc = nullptr; fin.ldmu = 0; fin.beta = lf.beta; fin.loss_rows = nullptr; fin.kl_rows = nullptr;
     if (lf.on) {
-        fin.lv = logvar; fin.ldlv = ldlv; fin.mu_loc = mu_all + (int64_t)row_offset * ldmu; fin.ldmu = ldmu;
+        fin.lv = logvar; fin.ldlv = ldlv; fin.mu_loc = peers.on() ? mu_all : mu_all + (int64_t)row_offset * ldmu; fin.ldmu = ldmu;
         fin.loss_rows = lf.loss_rows; fin.kl_rows = lf.kl_rows;
     }
     if ((e = launch_fwd_finalize(p, fin, st)) != cudaSuccess) return fail_cuda(e, "fwd_finalize");
@@ -182,8 +195,10 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
                          int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
                          const float* g_log_qz, const float* g_log_qz_prod, const LossFusion& lf,
                          float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
-                         const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream) {
+                         const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream,
+                         const Peers& peers = Peers()) {
     if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv)) return rc;
+    if (peers.on() && (flags & TCELBO_VAR_COL)) return fail(TCELBO_ERR_UNSUPPORTED, "the peer-memory exchange covers the row-variance density");
     if (!(flags & TCELBO_SAVE_FOR_BACKWARD)) return fail(TCELBO_ERR_INVALID, "backward needs the workspace of a forward run with TCELBO_SAVE_FOR_BACKWARD");
     if (!grad_z || !grad_mu_all || !grad_logvar) return fail(TCELBO_ERR_INVALID, "null gradient pointer");
     if (!lf.on && (!g_log_qz || !g_log_qz_prod)) return fail(TCELBO_ERR_INVALID, "null upstream gradient pointer");
@@ -216,7 +231,7 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
     float* Gpart = at<float>(scratch, p.boff_G);
 
     const size_t zero_n = (size_t)(p.var_col ? 2 : 1) * p.bg_pad * p.dp;
-    if ((e = launch_bwd_prep(p, g_log_qz, g_log_qz_prod, lf.g_loss, lf.g_kl, lf.beta, S, gps, gj, lf.on ? gk : nullptr,
+    if ((peers.phase & 1) && (e = launch_bwd_prep(p, g_log_qz, g_log_qz_prod, lf.g_loss, lf.g_kl, lf.beta, S, gps, gj, lf.on ? gk : nullptr,
                              Gpart, zero_n, st)) != cudaSuccess) return fail_cuda(e, "bwd_prep");
 
     BwdFinArgs fa;
@@ -225,11 +240,13 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
     fa.b_loc = b_loc; fa.b_glob = b_glob; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.d = d; fa.dp = p.dp;
     fa.n_js = 1; fa.n_is = 1;
     fa.gk = lf.on ? gk : nullptr; fa.lv = logvar; fa.ldlv = ldlv; fa.mu_all = mu_all; fa.ldmu = ldmu; fa.row_offset = row_offset;
+    fa.scratch_parts = peers.on() ? peers.scratch_parts : nullptr; fa.g_off = p.boff_G; fa.n_ranks = peers.n_ranks;
 
     BwdFusedArgs ua;
     ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
     ua.s2 = s2; ua.ld_s2 = p.ld_s2; ua.Apart = Apart; ua.CRpart = CRpart; ua.Gacc = Gpart; ua.Gacc2 = nullptr;
     ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = 0; ua.w = w;
+    ua.plan_only = (peers.phase & 1) ? 0 : 1;
 
     if (p.var_col) {
         float* Glv = Gpart + (size_t)p.bg_pad * p.dp;
@@ -240,6 +257,7 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
     }
     // single fused sweep: row-local sums in registers, column sums via smem staging + red.global
     if ((e = launch_bwd_fused(p, ua, &fa.n_js, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");
+    if (!(peers.phase & 2)) return TCELBO_OK;
     if ((e = launch_bwd_fused_finalize(p, fa, st)) != cudaSuccess) return fail_cuda(e, "bwd_fused_finalize");
     return TCELBO_OK;
 }
@@ -281,6 +299,37 @@ int tcelbo_klloss_backward(const float* z, int64_t ldz, const float* mu_all, int
     return backward_impl(z, ldz, mu_all, ldmu, logvar, ldlv, b_loc, b_glob, row_offset, d, dataset_size, flags,
                          g_log_qz, g_log_qz_prod, lf, grad_z, ldgz, grad_mu_all, ldgmu, grad_logvar, ldglv,
                          workspace, workspace_bytes, scratch, scratch_bytes, stream);
+}
+
+int tcelbo_klloss_forward_peer(const float* z, int64_t ldz, const float* mu_loc, int64_t ldmu, const float* const* mu_parts, int64_t ld_part,
+                               const float* logvar, int64_t ldlv, int b_loc, int n_ranks, int rank, int d, int64_t dataset_size,
+                               uint32_t flags, float beta, float* loss_rows, float* kl_rows, float* log_qz, float* log_qz_prod,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    if (!loss_rows || !kl_rows || !mu_parts) return fail(TCELBO_ERR_INVALID, "null pointer");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || ld_part < d) return fail(TCELBO_ERR_INVALID, "bad rank / n_ranks / ld_part");
+    if ((int64_t)b_loc * n_ranks > INT32_MAX) return fail(TCELBO_ERR_INVALID, "global batch too large");
+    LossFusion lf; lf.on = true; lf.beta = beta; lf.loss_rows = loss_rows; lf.kl_rows = kl_rows;
+    Peers peers; peers.mu_parts = mu_parts; peers.ld_part = ld_part; peers.n_ranks = n_ranks;
+    return forward_impl(z, ldz, mu_loc, ldmu, logvar, ldlv, b_loc, b_loc * n_ranks, rank * b_loc, d, dataset_size, flags,
+                        log_qz, log_qz_prod, lf, workspace, workspace_bytes, stream, peers);
+}
+
+int tcelbo_klloss_backward_peer(int phase, const float* z, int64_t ldz, const float* mu_loc, int64_t ldmu, const float* logvar, int64_t ldlv,
+                                int b_loc, int n_ranks, int rank, int d, int64_t dataset_size, uint32_t flags, float beta,
+                                const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
+                                float* grad_z, int64_t ldgz, float* grad_mu_loc, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
+                                const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
+                                const void* const* scratch_parts, void* stream) {
+    if (!g_loss_rows) return fail(TCELBO_ERR_INVALID, "null upstream gradient pointer");
+    if (phase != TCELBO_PEER_SWEEP && phase != TCELBO_PEER_FINISH) return fail(TCELBO_ERR_INVALID, "phase must be TCELBO_PEER_SWEEP or TCELBO_PEER_FINISH");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(TCELBO_ERR_INVALID, "bad rank / n_ranks");
+    if (phase == TCELBO_PEER_FINISH && !scratch_parts) return fail(TCELBO_ERR_INVALID, "null scratch table");
+    if ((int64_t)b_loc * n_ranks > INT32_MAX) return fail(TCELBO_ERR_INVALID, "global batch too large");
+    LossFusion lf; lf.on = true; lf.beta = beta; lf.g_loss = g_loss_rows; lf.g_kl = g_kl_rows;
+    Peers peers; peers.scratch_parts = scratch_parts; peers.n_ranks = n_ranks; peers.phase = phase;
+    return backward_impl(z, ldz, mu_loc, ldmu, logvar, ldlv, b_loc, b_loc * n_ranks, rank * b_loc, d, dataset_size, flags,
+                         g_log_qz, g_log_qz_prod, lf, grad_z, ldgz, grad_mu_loc, ldgmu, grad_logvar, ldglv,
+                         workspace, workspace_bytes, scratch, scratch_bytes, stream, peers);
 }
 
 #define ROWOP_CHECK(cond, msg) do { if (!(cond)) return fail(TCELBO_ERR_INVALID, msg); } while (0)

@@ -416,12 +416,30 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
 // and add the fused KL gradient when asked (ops.py:161-163).
 __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
     const int64_t n_row = (int64_t)a.b_loc * a.d;
-    const int64_t n_col = (int64_t)a.b_glob * a.d;
+    const int64_t n_col = a.scratch_parts != nullptr ? 0 : (int64_t)a.b_glob * a.d;
     const size_t split_stride = (size_t)a.bl_pad * a.dp;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_row + n_col; idx += (int64_t)gridDim.x * blockDim.x) {
         if (idx < n_row) {
             const int i = (int)(idx / a.d), dd = (int)(idx % a.d);
             const size_t o = (size_t)i * a.dp + dd;
+            if (a.scratch_parts != nullptr) {
+                // reduce-scatter of the column gradient as this kernel's load phase: the local rows of every rank's accumulator
+                const size_t og = (size_t)(a.row_offset + i) * a.dp + dd;
+                float g = 0.0f;
+                for (int p0 = 0; p0 < a.n_ranks; p0 += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        v[k] = (p0 + k < a.n_ranks)
+                                   ? *reinterpret_cast<const volatile float*>(static_cast<const char*>(a.scratch_parts[p0 + k]) + a.g_off + og * sizeof(float))
+                                   : 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) g += v[k];
+                }
+                g *= -kTwoLn2;
+                if (a.gk != nullptr) g += a.gk[i] * a.mu_all[(int64_t)i * a.ldmu + dd];      // mu_all = this rank's rows here
+                a.grad_mu[(int64_t)i * a.ldgmu + dd] = g;
+            }
             float sa = 0.0f, sc = 0.0f;
             for (int s0 = 0; s0 < a.n_js; s0 += 8) {
                 float va[8], vc[8];
@@ -478,6 +496,7 @@ static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, int* n_js_o
     a.pitch = p.dp;
     *n_js_out = n_js;
     const int n_slices = p.dp / GEO::DP;                                      // 1 unless a wide latent is walked in 128-dim slices
+    if (a.plan_only) return cudaSuccess;
     LaunchScope scope(kKernBwdRow, st);
     tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR><<<dim3(n_rb, n_js, n_slices), NW * 32, smem, st>>>(a);
     return cudaGetLastError();

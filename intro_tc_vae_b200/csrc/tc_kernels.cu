@@ -28,6 +28,22 @@ __global__ void col_prep_kernel(const float* __restrict__ mu_all, int64_t ldmu, 
     }
 }
 
+// Same, with the rows of mu living in `rows_per_part`-row blocks of different allocations (one per rank, peer-mapped):
+// the all-gather of the column operand is this kernel's load phase (coalesced 128-byte reads over NVLink).
+__global__ void col_prep_parts_kernel(const float* const* __restrict__ parts, int64_t ld_part, int rows_per_part, int b_glob, int d,
+                                      int bg_pad, int dp, float* __restrict__ mu_pad) {
+    const int64_t n = (int64_t)bg_pad * dp;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / dp), dd = (int)(idx % dp);
+        float v = 0.0f;
+        if (j < b_glob && dd < d) {
+            const int part = j / rows_per_part;
+            v = *static_cast<const volatile float*>(parts[part] + (int64_t)(j - part * rows_per_part) * ld_part + dd);   // no L1 / nc path
+        }
+        mu_pad[idx] = v;
+    }
+}
+
 __global__ void row_prep_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ logvar, int64_t ldlv,
                                 int b_loc, int d, int bl_pad, int dp,
                                 float* __restrict__ zs, float* __restrict__ ns, float* __restrict__ qmax,
@@ -360,6 +376,13 @@ cudaError_t launch_col_prep(const float* mu_all, int64_t ldmu, const Plan& p, fl
     const int64_t n = (int64_t)p.bg_pad * p.dp;
     LaunchScope scope(kKernNone, st);
     col_prep_kernel<<<grid_for(n, 256), 256, 0, st>>>(mu_all, ldmu, p.b_glob, p.d, p.bg_pad, p.dp, mu_pad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_col_prep_parts(const float* const* parts, int64_t ld_part, int rows_per_part, const Plan& p, float* mu_pad, cudaStream_t st) {
+    const int64_t n = (int64_t)p.bg_pad * p.dp;
+    LaunchScope scope(kKernNone, st);
+    col_prep_parts_kernel<<<grid_for(n, 256), 256, 0, st>>>(parts, ld_part, rows_per_part, p.b_glob, p.d, p.bg_pad, p.dp, mu_pad);
     return cudaGetLastError();
 }
 

@@ -37,6 +37,7 @@ struct BwdFusedArgs {
     float* Gacc2;                                                            // column-variance variant: logvar column sums
     int b_loc, bl_pad, bg_pad, row_offset, js_len;
     int pitch;                                                               // floats per row of the [*, dp] arrays
+    int plan_only;                                                           // host-side: compute the column split, launch nothing
     Weights w;
 };
 
@@ -47,9 +48,14 @@ struct BwdFinArgs {
     int b_loc, b_glob, bl_pad, bg_pad, d, dp, n_js, n_is;
     // optional fused KL gradient (ops.py:161-163): gk_i * mu on this rank's rows of grad_mu, gk_i * 0.5*(exp(lv)-1) on grad_lv
     const float* gk; const float* lv; int64_t ldlv; const float* mu_all; int64_t ldmu; int row_offset;
+    // peer-memory exchange: every rank's backward scratch (device table of n_ranks base pointers); the column sums of this
+    // rank's rows are read straight from the peers' accumulators and grad_mu covers the local rows only (nullptr: grad_mu_all)
+    const void* const* scratch_parts; size_t g_off; int n_ranks;
 };
 
 cudaError_t launch_col_prep(const float* mu_all, int64_t ldmu, const Plan& p, float* mu_pad, cudaStream_t st);
+// column operand read from n_parts equal row blocks in different allocations (peer GPUs' memory mapped over NVLink)
+cudaError_t launch_col_prep_parts(const float* const* parts, int64_t ld_part, int rows_per_part, const Plan& p, float* mu_pad, cudaStream_t st);
 cudaError_t launch_row_prep(const float* z, int64_t ldz, const float* logvar, int64_t ldlv, const Plan& p,
                             float* zs, float* ns, float* qmax, float* shift, float* vr, cudaStream_t st);
 cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st);

@@ -24,11 +24,30 @@ class GraphedKLLoss:
     tensors (or pinned host tensors: they are copied into the graph's static inputs on the current stream);
     the returned tensors are the graph's static outputs and are overwritten by the next call.
     ``group``: row-shard over the ranks of a process group (NCCL all-gather / reduce-scatter are captured too).
+    ``exchange="peer"``: do the two exchange steps over NVLink peer memory inside the library's kernels
+    (:mod:`intro_tc_vae_b200.peer`) instead of NCCL; ``"nccl"`` keeps the collectives; ``"auto"`` picks peer memory
+    when the group has more than one rank and symmetric memory can be set up, NCCL otherwise.
     """
 
     def __init__(self, b_loc: int, d: int, dataset_size: int, beta: float, device, group=None,
-                 estimator: str = "mss", warmup: int = 3):
+                 estimator: str = "mss", warmup: int = 3, exchange: str = "nccl"):
         self.device = torch.device(device)
+        self.exchange = None
+        self.exchange_kind = "none"
+        if group is not None:
+            import torch.distributed as dist
+            if dist.get_world_size(group) > 1:
+                self.exchange_kind = "nccl"
+                if exchange not in ("nccl", "peer", "auto"):
+                    raise ValueError(f"exchange must be 'nccl', 'peer' or 'auto', got {exchange!r}")
+                if exchange in ("peer", "auto"):
+                    from . import peer
+                    try:
+                        self.exchange = peer.PeerExchange(b_loc, d, group, self.device)
+                        self.exchange_kind = "peer"
+                    except Exception:
+                        if exchange == "peer":
+                            raise
         self.mu = torch.zeros(b_loc, d, device=self.device, requires_grad=True)
         self.logvar = torch.zeros(b_loc, d, device=self.device, requires_grad=True)
         self.eps = torch.zeros(b_loc, d, device=self.device)
@@ -56,7 +75,7 @@ class GraphedKLLoss:
         self.mu.grad = None
         self.logvar.grad = None
         z = ops.reparameterize(self.mu, self.logvar, self.eps)
-        loss = ops.kl_tc_loss_terms(z, self.mu, self.logvar, n, beta, estimator, group)[0].mean()
+        loss = ops.kl_tc_loss_terms(z, self.mu, self.logvar, n, beta, estimator, group, self.exchange)[0].mean()
         loss.backward()
         return loss.detach()
 

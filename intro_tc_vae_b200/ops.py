@@ -226,14 +226,16 @@ _klloss_forward.register_autograd(_klloss_autograd_backward, setup_context=_kllo
 
 
 def kl_tc_loss_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, beta: float, estimator: str = "mss",
-                     group=None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                     group=None, exchange=None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """One fused evaluation of ``TCSovler._compute_kl_loss_simple`` (solvers/tc.py:69-89) per sample:
 
         loss_i = (beta - 1) * (log_qz_i - log_qz_prod_i) + kl_i ,   kl_i = ops.py:161-163
 
     Returns ``(loss [B], kl [B], log_qz [B], log_qz_prod [B])``.  KL and the combine are folded into the TC
     kernels' finalize steps (forward and backward), so no separate KL or elementwise kernels are launched.
-    ``group`` row-shards the batch exactly as in :func:`tc_terms`.
+    ``group`` row-shards the batch exactly as in :func:`tc_terms` (NCCL all-gather / reduce-scatter around the kernels);
+    ``exchange`` (a :class:`intro_tc_vae_b200.peer.PeerExchange`) row-shards it over the exchange's group with both
+    exchange steps done by the library's kernels over NVLink peer memory instead.
     """
     for name, t in (("z", z), ("mu", mu), ("logvar", logvar)):
         _check(name, t)
@@ -245,6 +247,11 @@ def kl_tc_loss_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, b
     if torch.is_grad_enabled() and (z.requires_grad or mu.requires_grad or logvar.requires_grad):
         flags |= _lib.SAVE_FOR_BACKWARD
     row_offset, mu_all = 0, mu
+    if exchange is not None:
+        from .peer import kl_tc_loss_terms_peer
+        if estimator == "mss" and exchange.world * z.shape[0] == 1:
+            raise ZeroDivisionError("float division by zero")
+        return kl_tc_loss_terms_peer(z, mu, logvar, dataset_size, beta, flags, exchange)
     if group is not None:
         import torch.distributed as dist
         if dist.get_world_size(group) > 1:
