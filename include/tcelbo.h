@@ -170,6 +170,10 @@ int tcelbo_reparam_forward(const float* mu, int64_t ldmu, const float* logvar, i
 int tcelbo_reparam_backward(const float* logvar, int64_t ldlv, const float* eps, int64_t ldeps,
                             const float* g_z, int64_t ldgz, int b, int d,
                             float* grad_mu, int64_t ldgmu, float* grad_logvar, int64_t ldglv, void* stream);
+/* same, added to grad_mu / grad_logvar (which already hold the gradients of the loss terms that read mu and logvar directly) */
+int tcelbo_reparam_backward_acc(const float* logvar, int64_t ldlv, const float* eps, int64_t ldeps,
+                                const float* g_z, int64_t ldgz, int b, int d,
+                                float* grad_mu, int64_t ldgmu, float* grad_logvar, int64_t ldglv, void* stream);
 
 /*
  * Row-wise Gaussian log-density summed over D (ops.py:24-29 + .sum(dim=1), solvers/tc.py:107,112):

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "tcelbo_reparam_forward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_int64, c_void_p]),
     "tcelbo_reparam_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_int64, _f, c_int64,
                                         c_void_p]),
+    "tcelbo_reparam_backward_acc": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_int64, _f, c_int64,
+                                        c_void_p]),
     "tcelbo_rowdensity_forward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_void_p]),
     "tcelbo_rowdensity_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, _f, c_int, c_int,
                                            _f, c_int64, _f, c_int64, _f, c_int64, c_void_p]),

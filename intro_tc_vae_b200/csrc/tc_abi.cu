@@ -153,7 +153,7 @@ static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_
     float* shift = at<float>(workspace, p.off_shift);
     float* vr = at<float>(workspace, p.off_vr);
     float* Spart = at<float>(workspace, p.off_scratch);
-    float* Jpart = Spart + (size_t)p.n_js_fwd * p.bl_pad * p.dp;
+    float* Jpart = Spart + (size_t)p.n_part_fwd * p.bl_pad * p.dp;
 
     if (p.var_col) {
         if ((e = launch_colvar_prep(z, ldz, mu_all, ldmu, logvar, ldlv, p, mu_pad, zs, shift, st)) != cudaSuccess) return fail_cuda(e, "colvar_prep");
@@ -169,6 +169,7 @@ static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_
     fa.s2 = p.save ? at<float>(workspace, p.off_s2) : nullptr; fa.ld_s2 = p.ld_s2;
     fa.Spart = Spart; fa.Jpart = Jpart;
     fa.b_loc = b_loc; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.row_offset = row_offset; fa.js_len = p.js_len_fwd;
+    fa.seg = p.seg_fwd; fa.n_rb = p.n_rb_fwd;
     fa.w = w;
     int n_js_used = p.n_js_fwd;
     if (p.var_col) {
@@ -182,6 +183,8 @@ static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_
     fin.S = at<float>(workspace, p.off_S); fin.J2 = at<float>(workspace, p.off_J2);
     fin.log_qz = log_qz; fin.log_qz_prod = log_qz_prod;
     fin.b_loc = b_loc; fin.bl_pad = p.bl_pad; fin.d = d; fin.dp = p.dp; fin.n_js = n_js_used; fin.lw_u = w.lw_u;
+    fin.seg = p.seg_fwd; if (p.var_col) fin.seg.n_ctas = 0;
+    fin.tiles_per_block = p.tiles_fwd; fin.rows_per_block = p.fwd_rows;
     fin.lv = nullptr; fin.ldlv = 0; fin.mu_loc = nullptr; fin.ldmu = 0; fin.beta = lf.beta; fin.loss_rows = nullptr; fin.kl_rows = nullptr;
     if (lf.on) {
         fin.lv = logvar; fin.ldlv = ldlv; fin.mu_loc = peers.on() ? mu_all : mu_all + (int64_t)row_offset * ldmu; fin.ldmu = ldmu;
@@ -239,6 +242,7 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
     fa.grad_z = grad_z; fa.ldgz = ldgz; fa.grad_lv = grad_logvar; fa.ldglv = ldglv; fa.grad_mu = grad_mu_all; fa.ldgmu = ldgmu;
     fa.b_loc = b_loc; fa.b_glob = b_glob; fa.bl_pad = p.bl_pad; fa.bg_pad = p.bg_pad; fa.d = d; fa.dp = p.dp;
     fa.n_js = 1; fa.n_is = 1;
+    fa.seg = Segments{0, 0, 0}; fa.tiles_per_block = 0; fa.n_rb = 0; fa.rows_per_block = 0; fa.slice_dp = 0;
     fa.gk = lf.on ? gk : nullptr; fa.lv = logvar; fa.ldlv = ldlv; fa.mu_all = mu_all; fa.ldmu = ldmu; fa.row_offset = row_offset;
     fa.scratch_parts = peers.on() ? peers.scratch_parts : nullptr; fa.g_off = p.boff_G; fa.n_ranks = peers.n_ranks;
 
@@ -246,6 +250,7 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
     ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
     ua.s2 = s2; ua.ld_s2 = p.ld_s2; ua.Apart = Apart; ua.CRpart = CRpart; ua.Gacc = Gpart; ua.Gacc2 = nullptr;
     ua.b_loc = b_loc; ua.bl_pad = p.bl_pad; ua.bg_pad = p.bg_pad; ua.row_offset = row_offset; ua.js_len = 0; ua.w = w;
+    ua.seg = Segments{0, 0, 0}; ua.n_blocks = 0; ua.n_rb = 0;
     ua.plan_only = (peers.phase & 1) ? 0 : 1;
 
     if (p.var_col) {
@@ -256,7 +261,7 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
         return TCELBO_OK;
     }
     // single fused sweep: row-local sums in registers, column sums via smem staging + red.global
-    if ((e = launch_bwd_fused(p, ua, &fa.n_js, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");
+    if ((e = launch_bwd_fused(p, ua, &fa, st)) != cudaSuccess) return fail_cuda(e, "tc_bwd_fused");
     if (!(peers.phase & 2)) return TCELBO_OK;
     if ((e = launch_bwd_fused_finalize(p, fa, st)) != cudaSuccess) return fail_cuda(e, "bwd_fused_finalize");
     return TCELBO_OK;
@@ -361,7 +366,15 @@ int tcelbo_reparam_backward(const float* logvar, int64_t ldlv, const float* eps,
                             int b, int d, float* grad_mu, int64_t ldgmu, float* grad_logvar, int64_t ldglv, void* stream) {
     ROWOP_CHECK(logvar && eps && g_z && grad_mu && grad_logvar, "null pointer");
     ROWOP_CHECK(b >= 1 && d >= 1 && ldlv >= d && ldeps >= d && ldgz >= d && ldgmu >= d && ldglv >= d, "bad shape");
-    cudaError_t e = launch_reparam_bwd(logvar, ldlv, eps, ldeps, g_z, ldgz, b, d, grad_mu, ldgmu, grad_logvar, ldglv, static_cast<cudaStream_t>(stream));
+    cudaError_t e = launch_reparam_bwd(logvar, ldlv, eps, ldeps, g_z, ldgz, b, d, grad_mu, ldgmu, grad_logvar, ldglv, false, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "reparam_bwd");
+}
+
+int tcelbo_reparam_backward_acc(const float* logvar, int64_t ldlv, const float* eps, int64_t ldeps, const float* g_z, int64_t ldgz,
+                            int b, int d, float* grad_mu, int64_t ldgmu, float* grad_logvar, int64_t ldglv, void* stream) {
+    ROWOP_CHECK(logvar && eps && g_z && grad_mu && grad_logvar, "null pointer");
+    ROWOP_CHECK(b >= 1 && d >= 1 && ldlv >= d && ldeps >= d && ldgz >= d && ldgmu >= d && ldglv >= d, "bad shape");
+    cudaError_t e = launch_reparam_bwd(logvar, ldlv, eps, ldeps, g_z, ldgz, b, d, grad_mu, ldgmu, grad_logvar, ldglv, true, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "reparam_bwd");
 }
 
@@ -479,6 +492,8 @@ int tcelbo_profile_events(int kernel_id, void* start_event, void* stop_event) {
 
 int tcelbo_set_tuning(const char* key, int value) {
     if (key && std::strcmp(key, "bwd_variant") == 0) { set_bwd_variant(value); return TCELBO_OK; }
+    if (key && std::strcmp(key, "fwd_seg_tiles") == 0) { fwd_seg_target() = value; return TCELBO_OK; }
+    if (key && std::strcmp(key, "bwd_seg_tiles") == 0) { set_bwd_seg_target(value); return TCELBO_OK; }
     return fail(TCELBO_ERR_INVALID, "unknown tuning key");
 }
 

@@ -250,52 +250,87 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
     uint64_t* g_empty = g_full + NBUF;                                       // [NBUF] staging buffer reduced by all warps
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * ROWS + warp * RI;
-    // A CTA covers DP dims starting at d0 of rows whose pitch is a.pitch floats: for D > 128 the grid's z dimension walks
-    // 128-dim slices (row-local sums and column sums are independent per dim; only the joint coefficients are shared).
+    // Work = (latent slice, row block) blocks x T column tiles, linearised block-major and cut into equal contiguous
+    // segments of a.seg.base (+1) tiles, one per CTA (tc_layout.h: plan_segments): every CTA carries the same load whatever
+    // the batch shape; a segment that crosses a block boundary flushes its row-local sums and reloads the row constants.
+    // A block covers DP dims starting at d0 of rows whose pitch is a.pitch floats: for D > 128 the blocks walk 128-dim
+    // slices (row-local sums and column sums are independent per dim; only the joint coefficients are shared).
     const int pitch = a.pitch;
-    const int d0 = blockIdx.z * DP;
+    const int T = a.bg_pad / JT;
+    const int64_t g_begin = seg_begin(a.seg, blockIdx.x);
+    const int ntiles = seg_len(a.seg, blockIdx.x);
+    int q = (int)(g_begin / T);                                              // current block = slice * n_rb + row block
+    const int t_first = (int)(g_begin - (int64_t)q * T);                     // first column tile inside it
+    int rb0 = (q % a.n_rb) * ROWS;                                           // first row of the block
+    int row0 = rb0 + warp * RI;
+    int d0 = (q / a.n_rb) * DP;
 
     // ---- row constants and accumulators of this warp's RI rows (this lane's dims) -> registers.
     //      Rows past the padded batch are clamped for loads and carry zero coefficients.
     u64 zs2[RI][NP], ns2[RI][NP], gps2[RI][NP], A2[RI][NP], CR2[RI][NP];
     float qmx[RI][2 * NP];
+    auto load_rows = [&]() {
 #pragma unroll
-    for (int r = 0; r < RI; ++r) {
-        const bool valid = (row0 + r) < a.bl_pad;
-        const size_t base = (size_t)min(row0 + r, a.bl_pad - 1) * pitch + d0;
-        float vz[DPT], vn[DPT], vq[DPT], vg[DPT];
+        for (int r = 0; r < RI; ++r) {
+            const bool valid = (row0 + r) < a.bl_pad;
+            const size_t base = (size_t)min(row0 + r, a.bl_pad - 1) * pitch + d0;
+            float vz[DPT], vn[DPT], vq[DPT], vg[DPT];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            float v[VEC];
-            VecLd<VEC>::ld(a.zs + base + c * CH + VEC * lane, v);
+            for (int c = 0; c < NCH; ++c) {
+                float v[VEC];
+                VecLd<VEC>::ld(a.zs + base + c * CH + VEC * lane, v);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) vz[c * VEC + e] = v[e];
-            VecLd<VEC>::ld(a.ns + base + c * CH + VEC * lane, v);
+                for (int e = 0; e < VEC; ++e) vz[c * VEC + e] = v[e];
+                VecLd<VEC>::ld(a.ns + base + c * CH + VEC * lane, v);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) vn[c * VEC + e] = v[e];
-            VecLd<VEC>::ld(a.qmax + base + c * CH + VEC * lane, v);
+                for (int e = 0; e < VEC; ++e) vn[c * VEC + e] = v[e];
+                VecLd<VEC>::ld(a.qmax + base + c * CH + VEC * lane, v);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) vq[c * VEC + e] = v[e];
-            VecLd<VEC>::ld(a.gps + base + c * CH + VEC * lane, v);
+                for (int e = 0; e < VEC; ++e) vq[c * VEC + e] = v[e];
+                VecLd<VEC>::ld(a.gps + base + c * CH + VEC * lane, v);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) vg[c * VEC + e] = valid ? v[e] : 0.0f;
+                for (int e = 0; e < VEC; ++e) vg[c * VEC + e] = valid ? v[e] : 0.0f;
+            }
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const int e0 = 2 * p, e1 = (DPT >= 2) ? 2 * p + 1 : 0;
+                zs2[r][p] = pack2(vz[e0], DPT >= 2 ? vz[e1] : 0.0f);
+                ns2[r][p] = pack2(vn[e0], DPT >= 2 ? vn[e1] : 0.0f);
+                gps2[r][p] = pack2(vg[e0], DPT >= 2 ? vg[e1] : 0.0f);
+                qmx[r][2 * p] = vq[e0];
+                qmx[r][2 * p + 1] = DPT >= 2 ? vq[e1] : 0.0f;
+                A2[r][p] = 0ull; CR2[r][p] = 0ull;
+            }
         }
+    };
+    // row-local partial sums of the current block -> slot (this CTA's ordinal among the segments that touch the block)
+    auto flush_rows = [&]() {
+        const int slot = (int)blockIdx.x - seg_of(a.seg, (int64_t)q * T);
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            const int e0 = 2 * p, e1 = (DPT >= 2) ? 2 * p + 1 : 0;
-            zs2[r][p] = pack2(vz[e0], DPT >= 2 ? vz[e1] : 0.0f);
-            ns2[r][p] = pack2(vn[e0], DPT >= 2 ? vn[e1] : 0.0f);
-            gps2[r][p] = pack2(vg[e0], DPT >= 2 ? vg[e1] : 0.0f);
-            qmx[r][2 * p] = vq[e0];
-            qmx[r][2 * p + 1] = DPT >= 2 ? vq[e1] : 0.0f;
-            A2[r][p] = 0ull; CR2[r][p] = 0ull;
+        for (int r = 0; r < RI; ++r) {
+            if (row0 + r >= a.bl_pad) continue;
+            const size_t base = ((size_t)slot * a.bl_pad + row0 + r) * pitch + d0;
+            float va[DPT], vc[DPT];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                float lo, hi;
+                unpack2(A2[r][p], lo, hi); va[2 * p % DPT] = lo; if (DPT >= 2) va[(2 * p + 1) % DPT] = hi;
+                unpack2(CR2[r][p], lo, hi); vc[2 * p % DPT] = lo; if (DPT >= 2) vc[(2 * p + 1) % DPT] = hi;
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float v[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v[e] = va[c * VEC + e];
+                VecLd<VEC>::st(a.Apart + base + c * CH + VEC * lane, v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v[e] = vc[c * VEC + e];
+                VecLd<VEC>::st(a.CRpart + base + c * CH + VEC * lane, v);
+            }
         }
-    }
+    };
+    load_rows();
 
-    const int j0 = blockIdx.y * a.js_len;
-    const int j1 = min(a.bg_pad, j0 + a.js_len);
-    const int ntiles = (j1 - j0) / JT;
     constexpr uint32_t kTxBytes = (TILE + ROWS * JT) * sizeof(float);
 
     if (threadIdx.x == 0) {
@@ -305,29 +340,31 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
     }
     __syncthreads();
 
-    auto issue = [&](int t) {                                                // warp 0, all lanes
+    // warp 0, all lanes; t = tile ordinal in the segment, tn = its column tile inside block (first row rbn, slice offset dn)
+    auto issue = [&](int t, int tn, int rbn, int dn) {
         const int sn = t % kStages;
+        const int jn = tn * JT;
         if (lane == 0) {
             if (t >= kStages) mbar_wait(&bar_empty[sn], ((t / kStages) - 1) & 1);
             mbar_arrive_expect_tx(&bar_full[sn], kTxBytes);
             if (pitch == DP)                                                 // whole rows: one contiguous bulk copy
-                bulk_g2s(mu_tiles + (size_t)sn * TILE, a.mu_pad + (size_t)(j0 + t * JT) * DP, TILE * sizeof(float), &bar_full[sn]);
+                bulk_g2s(mu_tiles + (size_t)sn * TILE, a.mu_pad + (size_t)jn * DP, TILE * sizeof(float), &bar_full[sn]);
         }
         __syncwarp();
         if (pitch != DP) {                                                   // a 128-dim slice of wider rows: one copy per column
             for (int c = lane; c < JT; c += 32)
-                bulk_g2s(mu_tiles + (size_t)sn * TILE + (size_t)c * DP, a.mu_pad + (size_t)(j0 + t * JT + c) * pitch + d0,
+                bulk_g2s(mu_tiles + (size_t)sn * TILE + (size_t)c * DP, a.mu_pad + (size_t)(jn + c) * pitch + dn,
                          DP * sizeof(float), &bar_full[sn]);
         }
         for (int r = lane; r < ROWS; r += 32)
             bulk_g2s(s2_tiles + ((size_t)sn * ROWS + r) * JT,
-                     a.s2 + (size_t)min((int)(blockIdx.x * ROWS + r), a.bl_pad - 1) * a.ld_s2 + (j0 + t * JT), JT * sizeof(float), &bar_full[sn]);
+                     a.s2 + (size_t)min(rbn + r, a.bl_pad - 1) * a.ld_s2 + jn, JT * sizeof(float), &bar_full[sn]);
     };
-    if (warp == 0 && ntiles > 0) issue(0);
+    if (warp == 0 && ntiles > 0) issue(0, t_first, rb0, d0);
 
     // reduce this thread's share of staging buffer (k & 1) (sub-tile k, columns starting at col0) into Gacc
     // With NBUF >= 3 a warp may run a whole sub-tile ahead of the slowest warp of its CTA before it blocks here.
-    auto reduce_share = [&](int k, int col0) {
+    auto reduce_share = [&](int k, int col0, int dd0) {
         const int b = k % NBUF;
         mbar_wait(&g_full[b], (k / NBUF) & 1);
         const float* gsb = gstage + (size_t)b * GST;
@@ -339,21 +376,32 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
                 const float4 v = *reinterpret_cast<const float4*>(gsb + ((size_t)w * JS + col) * DP + 4 * chunk);
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
-            red_add_v4(a.Gacc + (size_t)(col0 + col) * pitch + d0 + 4 * chunk, acc.x, acc.y, acc.z, acc.w);
+            red_add_v4(a.Gacc + (size_t)(col0 + col) * pitch + dd0 + 4 * chunk, acc.x, acc.y, acc.z, acc.w);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&g_empty[b]);
     };
 
     float* gq = gq_buf + (size_t)warp * RI * JT;
-    int k = 0, prev_col0 = 0;                                                // running sub-tile index
-    for (int t = 0; t < ntiles; ++t) {
+    int k = 0, prev_col0 = 0, prev_d0 = 0;                                   // running sub-tile index
+    int t_in = t_first;                                                      // column tile inside the current block
+    for (int t = 0; t < ntiles; ++t, ++t_in) {
+        if (t_in == T) {                                                     // segment crosses into the next block
+            flush_rows();
+            ++q; t_in = 0;
+            rb0 = (q % a.n_rb) * ROWS; row0 = rb0 + warp * RI; d0 = (q / a.n_rb) * DP;
+            load_rows();
+        }
         const int st = t % kStages;
-        if (warp == 0 && t + 1 < ntiles) issue(t + 1);
+        if (warp == 0 && t + 1 < ntiles) {                                   // prefetch the next tile (possibly of the next block)
+            int tn = t_in + 1, rbn = rb0, dn = d0;
+            if (tn == T) { tn = 0; rbn = ((q + 1) % a.n_rb) * ROWS; dn = ((q + 1) / a.n_rb) * DP; }
+            issue(t + 1, tn, rbn, dn);
+        }
         mbar_wait(&bar_full[st], (t / kStages) & 1);
         const float* tile = mu_tiles + (size_t)st * TILE;
         const float* s2t = s2_tiles + ((size_t)st * ROWS + warp * RI) * JT;
-        const int jt0 = j0 + t * JT;
+        const int jt0 = t_in * JT;
         const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
 
         // joint-term coefficients gJ_i * q_ij of this warp's rows for the tile
@@ -379,37 +427,14 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
             if (ABL == 1) continue;                                  // timing ablation: no staging hand-off / reduction
             __syncwarp();
             if (lane == 0) mbar_arrive(&g_full[b]);
-            if (k >= 1) reduce_share(k - 1, prev_col0);                      // the other buffer: its writers are long done
-            prev_col0 = jt0 + sub;
+            if (k >= 1) reduce_share(k - 1, prev_col0, prev_d0);             // the other buffer: its writers are long done
+            prev_col0 = jt0 + sub; prev_d0 = d0;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[st]);
     }
-    if (ABL != 1 && k >= 1) reduce_share(k - 1, prev_col0);
-
-    // ---- row-local partial sums of this (row block, column split)
-#pragma unroll
-    for (int r = 0; r < RI; ++r) {
-        if (row0 + r >= a.bl_pad) continue;
-        const size_t base = ((size_t)blockIdx.y * a.bl_pad + row0 + r) * pitch + d0;
-        float va[DPT], vc[DPT];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            float lo, hi;
-            unpack2(A2[r][p], lo, hi); va[2 * p % DPT] = lo; if (DPT >= 2) va[(2 * p + 1) % DPT] = hi;
-            unpack2(CR2[r][p], lo, hi); vc[2 * p % DPT] = lo; if (DPT >= 2) vc[(2 * p + 1) % DPT] = hi;
-        }
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            float v[VEC];
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) v[e] = va[c * VEC + e];
-            VecLd<VEC>::st(a.Apart + base + c * CH + VEC * lane, v);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) v[e] = vc[c * VEC + e];
-            VecLd<VEC>::st(a.CRpart + base + c * CH + VEC * lane, v);
-        }
-    }
+    if (ABL != 1 && k >= 1) reduce_share(k - 1, prev_col0, prev_d0);
+    flush_rows();
 }
 
 // Elementwise over [B,D]: sum the column-split partials of the row-local sums (8 independent loads in flight), scale,
@@ -441,11 +466,14 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
                 a.grad_mu[(int64_t)i * a.ldgmu + dd] = g;
             }
             float sa = 0.0f, sc = 0.0f;
-            for (int s0 = 0; s0 < a.n_js; s0 += 8) {
+            // partial slots of this (slice, row block): one per segment that touches the block
+            const int64_t qb = (int64_t)(dd / a.slice_dp) * a.n_rb + i / a.rows_per_block;
+            const int n_slots = seg_slots(a.seg, qb, a.tiles_per_block);
+            for (int s0 = 0; s0 < n_slots; s0 += 8) {
                 float va[8], vc[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const bool ok = s0 + k < a.n_js;
+                    const bool ok = s0 + k < n_slots;
                     va[k] = ok ? __ldg(a.Apart + (size_t)(s0 + k) * split_stride + o) : 0.0f;
                     vc[k] = ok ? __ldg(a.CRpart + (size_t)(s0 + k) * split_stride + o) : 0.0f;
                 }
@@ -472,9 +500,11 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
 // ------------------------------------------------------------------------------------------------------
 static int g_bwd_variant = -1;      // -1: default per shape; set through tcelbo_set_tuning("bwd_variant", v)
 void set_bwd_variant(int v) { g_bwd_variant = v; }
+static int g_bwd_seg_target = 0;    // 0: default target segment length (column tiles per CTA)
+void set_bwd_seg_target(int v) { g_bwd_seg_target = v; }
 
 template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF = 2, int ABL = 0, bool SCALAR = false>
-static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, int* n_js_out, cudaStream_t st) {
+static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, BwdFinArgs* fin, cudaStream_t st) {
     using GEO = BwdGeom<DPT, JS_>;
     constexpr int ROWS = NW * RI;
     const size_t smem = ((size_t)kStages * GEO::JT * GEO::DP + (size_t)kStages * ROWS * GEO::JT + (size_t)NW * RI * GEO::JT
@@ -490,37 +520,38 @@ static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, int* n_js_o
         ctas_per_sm = occ > 0 ? occ : 1;
     }
     const int n_rb = (p.bl_pad + ROWS - 1) / ROWS;
-    int n_js, js_len;
-    choose_splits(n_rb * (p.dp / GEO::DP), p.sms * ctas_per_sm, p.bg_pad, GEO::JT, 4, n_js, js_len);
-    a.js_len = js_len;
-    a.pitch = p.dp;
-    *n_js_out = n_js;
     const int n_slices = p.dp / GEO::DP;                                      // 1 unless a wide latent is walked in 128-dim slices
+    const int T = p.bg_pad / GEO::JT;
+    const Segments seg = plan_segments((int64_t)n_rb * n_slices, T, p.sms * ctas_per_sm, g_bwd_seg_target > 0 ? g_bwd_seg_target : 64);
+    a.js_len = 0;
+    a.pitch = p.dp;
+    a.seg = seg; a.n_blocks = n_rb * n_slices; a.n_rb = n_rb;
+    fin->seg = seg; fin->tiles_per_block = T; fin->n_rb = n_rb; fin->rows_per_block = ROWS; fin->slice_dp = GEO::DP;
     if (a.plan_only) return cudaSuccess;
     LaunchScope scope(kKernBwdRow, st);
-    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR><<<dim3(n_rb, n_js, n_slices), NW * 32, smem, st>>>(a);
+    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR><<<seg.n_ctas, NW * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out, cudaStream_t st) {
+cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* fin, cudaStream_t st) {
     switch (p.dpt) {
-        case 1:  return launch_bwd_fused_t<1, 4, 12, 1, 8, false>(p, a, n_js_out, st);
-        case 2:  return launch_bwd_fused_t<2, 4, 12, 1, 8, false>(p, a, n_js_out, st);
+        case 1:  return launch_bwd_fused_t<1, 4, 12, 1, 8, false>(p, a, fin, st);
+        case 2:  return launch_bwd_fused_t<2, 4, 12, 1, 8, false>(p, a, fin, st);
         case 4:
             switch (g_bwd_variant) {                 // tuning matrix for the headline shape (D = 128); see profiles/r1_bwd_variant_sweep.md
-                case 0:  return launch_bwd_fused_t<4, 4, 12, 1, 8, false>(p, a, n_js_out, st);            // 12 warps x 168 regs, 1 CTA/SM
-                case 1:  return launch_bwd_fused_t<4, 4, 12, 1, 8, true >(p, a, n_js_out, st);            //   + two-phase loop body
-                case 2:  return launch_bwd_fused_t<4, 4, 8, 2, 8, false>(p, a, n_js_out, st);             // 4 rows/warp, 2 CTAs/SM (spills)
-                case 4:  return launch_bwd_fused_t<4, 2, 8, 3, 4, false>(p, a, n_js_out, st);             // 2 rows/warp, 3 CTAs/SM
-                case 11: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 3>(p, a, n_js_out, st);          // three staging buffers
-                case 30: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, true>(p, a, n_js_out, st); // scalar predicated loop
-                case 20: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 1>(p, a, n_js_out, st);       // ablation: no column-gradient path
-                case 21: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 2>(p, a, n_js_out, st);       // ablation: no MUFU
-                case 22: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 3>(p, a, n_js_out, st);       // ablation: no joint-coefficient loads
-                default: return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);             // best of the sweep
+                case 0:  return launch_bwd_fused_t<4, 4, 12, 1, 8, false>(p, a, fin, st);            // 12 warps x 168 regs, 1 CTA/SM
+                case 1:  return launch_bwd_fused_t<4, 4, 12, 1, 8, true >(p, a, fin, st);            //   + two-phase loop body
+                case 2:  return launch_bwd_fused_t<4, 4, 8, 2, 8, false>(p, a, fin, st);             // 4 rows/warp, 2 CTAs/SM (spills)
+                case 4:  return launch_bwd_fused_t<4, 2, 8, 3, 4, false>(p, a, fin, st);             // 2 rows/warp, 3 CTAs/SM
+                case 11: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 3>(p, a, fin, st);          // three staging buffers
+                case 30: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, true>(p, a, fin, st); // scalar predicated loop
+                case 20: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 1>(p, a, fin, st);       // ablation: no column-gradient path
+                case 21: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 2>(p, a, fin, st);       // ablation: no MUFU
+                case 22: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 3>(p, a, fin, st);       // ablation: no joint-coefficient loads
+                default: return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, fin, st);             // best of the sweep
             }
         case 8: case 16:                             // D = 256 / 512: the tuned 128-dim kernel over 2 / 4 slices (grid.z)
-            return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, n_js_out, st);
+            return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, fin, st);
         default: return cudaErrorInvalidValue;
     }
 }

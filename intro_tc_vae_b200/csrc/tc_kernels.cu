@@ -164,14 +164,22 @@ tc_fwd_kernel(const FwdArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int l = lane % LPR, rw = lane / LPR;
-    const int row = blockIdx.x * ROWS + warp * RPW + rw;                     // < bl_pad by construction
-    const int i_glob = a.row_offset + row;
+    // Work = row blocks x T column tiles, linearised block-major and cut into equal contiguous segments of a.seg_tiles
+    // (+1) tiles, one per CTA (tc_layout.h: plan_segments): every CTA carries the same load whatever the batch shape.  A
+    // segment that crosses into the next row block flushes its partial sums and reloads the row constants.
+    const int T = a.bg_pad / JT;
+    const int64_t g_begin = seg_begin(a.seg, blockIdx.x);
+    const int ntiles = seg_len(a.seg, blockIdx.x);
+    int rb = (int)(g_begin / T);
+    int t_in = (int)(g_begin - (int64_t)rb * T);                             // column tile inside the current row block
+    int row = rb * ROWS + warp * RPW + rw;                                   // < bl_pad by construction
     const bool row_valid = true;   // padded rows hold finite zeros: store their s2 too so backward never reads garbage
 
-    // ---- this thread's slice of the row constants -> registers
     u64 zs2[16], ns2[16], S2[16];
     float qmx[32];
-    {
+    float lse_m = kNegBig, lse_s = 0.0f;
+    // ---- this thread's slice of the row constants -> registers
+    auto load_row = [&]() {
         const float* pz = a.zs + (size_t)row * DP + 4 * l;
         const float* pn = a.ns + (size_t)row * DP + 4 * l;
         const float* pq = a.qmax + (size_t)row * DP + 4 * l;
@@ -185,46 +193,12 @@ tc_fwd_kernel(const FwdArgs a) {
             qmx[4 * k] = vq.x; qmx[4 * k + 1] = vq.y; qmx[4 * k + 2] = vq.z; qmx[4 * k + 3] = vq.w;
             S2[2 * k] = 0ull; S2[2 * k + 1] = 0ull;
         }
-    }
-    float lse_m = kNegBig, lse_s = 0.0f;
-
-    const int j0 = blockIdx.y * a.js_len;
-    const int j1 = min(a.bg_pad, j0 + a.js_len);
-    const int ntiles = (j1 - j0) / JT;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kFwdWarps); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && ntiles > 0) {
-        mbar_arrive_expect_tx(&bar_full[0], TILE * sizeof(float));
-        bulk_g2s(tiles, a.mu_pad + (size_t)j0 * DP, TILE * sizeof(float), &bar_full[0]);
-    }
-
-    float* s2_row = (a.s2 != nullptr) ? a.s2 + (size_t)row * a.ld_s2 : nullptr;
-
-    for (int t = 0; t < ntiles; ++t) {
-        const int st = t % kStages;
-        if (threadIdx.x == 0 && t + 1 < ntiles) {                              // prefetch tile t+1
-            const int sn = (t + 1) % kStages;
-            if (t + 1 >= kStages) mbar_wait(&bar_empty[sn], (((t + 1) / kStages) - 1) & 1);
-            mbar_arrive_expect_tx(&bar_full[sn], TILE * sizeof(float));
-            bulk_g2s(tiles + (size_t)sn * TILE, a.mu_pad + (size_t)(j0 + (t + 1) * JT) * DP, TILE * sizeof(float), &bar_full[sn]);
-        }
-        mbar_wait(&bar_full[st], (t / kStages) & 1);
-        const float* tile = tiles + (size_t)st * TILE;
-        const int jt0 = j0 + t * JT;
-        const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
-        if (special) fwd_tile<LPR, true>(tile, JT, jt0, l, i_glob, row_valid, a.w, zs2, ns2, qmx, S2, lse_m, lse_s, s2_row);
-        else         fwd_tile<LPR, false>(tile, JT, jt0, l, i_glob, row_valid, a.w, zs2, ns2, qmx, S2, lse_m, lse_s, s2_row);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_empty[st]);
-    }
-
-    // ---- partial results of this (row block, column split)
-    {
-        float* ps = a.Spart + ((size_t)blockIdx.y * a.bl_pad + row) * DP + 4 * l;
+        lse_m = kNegBig; lse_s = 0.0f;
+    };
+    // ---- partial results of the current row block -> slot (this CTA's ordinal among the segments that touch the block)
+    auto flush_row = [&]() {
+        const int slot = (int)blockIdx.x - seg_of(a.seg, (int64_t)rb * T);
+        float* ps = a.Spart + ((size_t)slot * a.bl_pad + row) * DP + 4 * l;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float4 v;
@@ -238,10 +212,48 @@ tc_fwd_kernel(const FwdArgs a) {
             lse2_merge(lse_m, lse_s, m2, s2v);
         }
         if (l == 0) {
-            float2* pj = reinterpret_cast<float2*>(a.Jpart) + (size_t)blockIdx.y * a.bl_pad + row;
+            float2* pj = reinterpret_cast<float2*>(a.Jpart) + (size_t)slot * a.bl_pad + row;
             *pj = make_float2(lse_m, lse_s);
         }
+    };
+    load_row();
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kFwdWarps); }
+        mbar_fence_init();
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && ntiles > 0) {
+        mbar_arrive_expect_tx(&bar_full[0], TILE * sizeof(float));
+        bulk_g2s(tiles, a.mu_pad + (size_t)t_in * TILE, TILE * sizeof(float), &bar_full[0]);
+    }
+
+    for (int t = 0; t < ntiles; ++t, ++t_in) {
+        if (t_in == T) {                                                       // segment crosses into the next row block
+            flush_row();
+            ++rb; t_in = 0; row += ROWS;
+            load_row();
+        }
+        const int st = t % kStages;
+        if (threadIdx.x == 0 && t + 1 < ntiles) {                              // prefetch tile t+1 (column tiles wrap at a block boundary)
+            const int sn = (t + 1) % kStages;
+            const int tn = (t_in + 1 == T) ? 0 : t_in + 1;
+            if (t + 1 >= kStages) mbar_wait(&bar_empty[sn], (((t + 1) / kStages) - 1) & 1);
+            mbar_arrive_expect_tx(&bar_full[sn], TILE * sizeof(float));
+            bulk_g2s(tiles + (size_t)sn * TILE, a.mu_pad + (size_t)tn * TILE, TILE * sizeof(float), &bar_full[sn]);
+        }
+        mbar_wait(&bar_full[st], (t / kStages) & 1);
+        const float* tile = tiles + (size_t)st * TILE;
+        const int jt0 = t_in * JT;
+        const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
+        float* s2_row = (a.s2 != nullptr) ? a.s2 + (size_t)row * a.ld_s2 : nullptr;
+        const int i_glob = a.row_offset + row;
+        if (special) fwd_tile<LPR, true>(tile, JT, jt0, l, i_glob, row_valid, a.w, zs2, ns2, qmx, S2, lse_m, lse_s, s2_row);
+        else         fwd_tile<LPR, false>(tile, JT, jt0, l, i_glob, row_valid, a.w, zs2, ns2, qmx, S2, lse_m, lse_s, s2_row);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[st]);
+    }
+    flush_row();
 }
 
 // One warp per row: sum the column-split partials (float4 per lane, 8 independent loads in flight), take logs,
@@ -252,14 +264,17 @@ __global__ void fwd_finalize_kernel(const FinArgs a) {
     if (row >= a.b_loc) return;
     float P = 0.0f, C = 0.0f;
     const size_t split_stride = (size_t)a.bl_pad * a.dp;
+    int n_js = a.n_js;                                     // uniform column split, or (balanced segments) the number of
+    if (a.seg.n_ctas > 0)                                  // segments that touch this row's block
+        n_js = seg_slots(a.seg, row / a.rows_per_block, a.tiles_per_block);
     for (int d0 = 4 * lane; d0 < a.dp; d0 += 128) {
         const float* src = a.Spart + (size_t)row * a.dp + d0;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s0 = 0; s0 < a.n_js; s0 += 8) {
+        for (int s0 = 0; s0 < n_js; s0 += 8) {
             float4 v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                v[k] = (s0 + k < a.n_js) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(s0 + k) * split_stride))
+                v[k] = (s0 + k < n_js) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(s0 + k) * split_stride))
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
@@ -288,7 +303,7 @@ __global__ void fwd_finalize_kernel(const FinArgs a) {
     if (lane == 0) {
         const float2* pj = reinterpret_cast<const float2*>(a.Jpart);
         float m = kNegBig, s = 0.0f;
-        for (int k = 0; k < a.n_js; ++k) {
+        for (int k = 0; k < n_js; ++k) {
             const float2 v = pj[(size_t)k * a.bl_pad + row];
             const float mn = fmaxf(m, v.x);
             s = s * exp2f(m - mn) + v.y * exp2f(v.x - mn);
@@ -368,7 +383,7 @@ static cudaError_t launch_fwd_t(const Plan& p, const FwdArgs& a, cudaStream_t st
         configured = true;
     }
     LaunchScope scope(kKernFwd, st);
-    tc_fwd_kernel<LPR><<<dim3(p.n_rb_fwd, p.n_js_fwd), kFwdWarps * 32, smem, st>>>(a);
+    tc_fwd_kernel<LPR><<<p.seg_fwd.n_ctas, kFwdWarps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -14,6 +14,7 @@ struct FwdArgs {
     float* Spart;                                          // [n_js][bl_pad][dp]
     float* Jpart;                                          // [n_js][bl_pad] (m, s) pairs
     int b_loc, bl_pad, bg_pad, row_offset, js_len;
+    Segments seg; int n_rb;                                // balanced segments (row-variance sweep; tc_layout.h: plan_segments)
     Weights w;
 };
 
@@ -21,6 +22,7 @@ struct FinArgs {
     const float* Spart; const float* Jpart; const float* shift;
     float* S; float* J2; float* log_qz; float* log_qz_prod;
     int b_loc, bl_pad, d, dp, n_js;
+    Segments seg; int tiles_per_block, rows_per_block;     // seg.n_ctas > 0: per-row slot count from the segment plan instead of n_js
     float lw_u;
     // optional fusion of solvers/tc.py:83-89: kl_i (ops.py:161-163) and loss_i = (beta-1)*(log_qz-log_qz_prod) + kl_i
     const float* lv; int64_t ldlv; const float* mu_loc; int64_t ldmu;   // this rank's rows of logvar / mu (nullptr: no fusion)
@@ -37,6 +39,7 @@ struct BwdFusedArgs {
     float* Gacc2;                                                            // column-variance variant: logvar column sums
     int b_loc, bl_pad, bg_pad, row_offset, js_len;
     int pitch;                                                               // floats per row of the [*, dp] arrays
+    Segments seg; int n_blocks, n_rb;                                        // balanced segments (fused sweep; tc_layout.h: plan_segments)
     int plan_only;                                                           // host-side: compute the column split, launch nothing
     Weights w;
 };
@@ -46,6 +49,8 @@ struct BwdFinArgs {
     const float* ns; const float* vr;
     float* grad_z; int64_t ldgz; float* grad_lv; int64_t ldglv; float* grad_mu; int64_t ldgmu;
     int b_loc, b_glob, bl_pad, bg_pad, d, dp, n_js, n_is;
+    // fused sweep: the partial slots of a row come from the segments that touch its (slice, row block) block
+    Segments seg; int tiles_per_block, n_rb, rows_per_block, slice_dp;
     // optional fused KL gradient (ops.py:161-163): gk_i * mu on this rank's rows of grad_mu, gk_i * 0.5*(exp(lv)-1) on grad_lv
     const float* gk; const float* lv; int64_t ldlv; const float* mu_all; int64_t ldmu; int row_offset;
     // peer-memory exchange: every rank's backward scratch (device table of n_ranks base pointers); the column sums of this
@@ -64,8 +69,9 @@ cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st
 // writes gps = gP/S, gj = gJ, gk = g_loss + g_kl (if gk != null) and zeroes `zero_n` floats at `zero` (the column accumulator).
 cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g_log_qz_prod, const float* g_loss, const float* g_kl,
                             float beta, const float* S, float* gps, float* gj, float* gk, float* zero, size_t zero_n, cudaStream_t st);
-cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, int* n_js_out, cudaStream_t st);
+cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* fin, cudaStream_t st);   // fills fin's segment fields
 void set_bwd_variant(int v);
+void set_bwd_seg_target(int v);
 // column-variance ("full" path) variant, tc_colvar.cu
 cudaError_t launch_colvar_prep(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* lv_all, int64_t ldlv,
                                const Plan& p, float* colpack, float* zpad, float* shift, cudaStream_t st);

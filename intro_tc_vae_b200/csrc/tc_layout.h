@@ -14,6 +14,33 @@ constexpr int kBwdWarps   = 8;
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+constexpr int kMaxSplits = 16;        // upper bound on the partial-sum slots per row block (bounds the scratch)
+
+// Balanced segments: a sweep's work is n_blocks row blocks x tiles_per_block column tiles.  Linearised block-major
+// and cut into n_ctas contiguous segments whose lengths differ by at most one tile (one CTA each, n_ctas a whole number
+// of waves of resident CTA slots), every CTA carries the same load for any batch shape -- a uniform (row block x
+// column split) grid loses up to a full wave when n_blocks * n_splits lands just above a multiple of the slots (15 %
+// of the backward sweep at 1024 rows per GPU).  A segment that crosses a block boundary writes one partial slot per
+// block it touches; at most kMaxSplits segments touch a block.
+#ifdef __CUDACC__
+#define TCELBO_HD __host__ __device__
+#else
+#define TCELBO_HD
+#endif
+struct Segments {
+    int n_ctas, base, rem;            // segments 0..rem-1 hold base+1 tiles, the others base tiles
+};
+TCELBO_HD inline int64_t seg_begin(const Segments& s, int c) { return (int64_t)c * s.base + (c < s.rem ? c : s.rem); }
+TCELBO_HD inline int seg_len(const Segments& s, int c) { return s.base + (c < s.rem ? 1 : 0); }
+TCELBO_HD inline int seg_of(const Segments& s, int64_t g) {           // the segment that holds tile g
+    const int64_t cut = (int64_t)s.rem * (s.base + 1);
+    return g < cut ? (int)(g / (s.base + 1)) : s.rem + (int)((g - cut) / s.base);
+}
+// number of segments that touch block q (tiles [q*T, (q+1)*T))
+TCELBO_HD inline int seg_slots(const Segments& s, int64_t q, int tiles_per_block) {
+    return seg_of(s, (q + 1) * tiles_per_block - 1) - seg_of(s, q * tiles_per_block) + 1;
+}
+
 struct Plan {
     // padded problem
     int sms;
@@ -21,7 +48,9 @@ struct Plan {
     int b_loc, b_glob, bl_pad, bg_pad;
     int jt;                    // column-tile height (rows of mu per stage) = kTileFloats / dp
     // forward sweep: grid (n_rb_fwd, n_js_fwd)
-    int fwd_rows, n_rb_fwd, n_js_fwd, js_len_fwd;
+    int fwd_rows, n_rb_fwd, n_js_fwd, js_len_fwd;            // uniform split (column-variance sweep)
+    Segments seg_fwd; int tiles_fwd, slots_fwd;               // balanced segments (row-variance sweep)
+    int n_part_fwd;                                           // partial-sum slots the scratch holds
     // workspace (byte offsets)
     size_t off_mu, off_zs, off_ns, off_qmax, off_shift, off_vr;   // [bg_pad|bl_pad][dp]
     size_t off_S, off_J2;                                         // persistent forward results
@@ -35,7 +64,6 @@ struct Plan {
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-constexpr int kMaxSplits = 16;        // upper bound on column/row splits (bounds the partial-sum scratch)
 
 // Pick how many ranges to cut `len` (a multiple of `quantum`) into so that n_blocks * n_splits CTAs fill
 // `slots` resident CTA slots in whole waves: minimises ceil(ctas / slots) / n_splits, i.e. the time of
@@ -57,6 +85,24 @@ inline void choose_splits(int n_blocks, int slots, int len, int quantum, int min
     n_splits = (len + split_len - 1) / split_len;
 }
 
+inline Segments plan_segments(int64_t n_blocks, int tiles_per_block, int slots, int target_tiles) {
+    const int64_t total = n_blocks * tiles_per_block;
+    int64_t min_seg = (tiles_per_block - 1 + (kMaxSplits - 3)) / (kMaxSplits - 2);   // (T-1)/base + 2 <= kMaxSplits
+    if (min_seg < 4) min_seg = tiles_per_block < 4 ? tiles_per_block : 4;
+    const int64_t want = target_tiles > min_seg ? target_tiles : min_seg;
+    int64_t waves = (total + (int64_t)slots * want / 2) / ((int64_t)slots * want);    // nearest whole number of waves
+    if (waves < 1) waves = 1;
+    int64_t n = (int64_t)slots * waves;
+    while (waves > 1 && total / n < min_seg) { --waves; n = (int64_t)slots * waves; }
+    if (total / n < min_seg) n = total / min_seg;                                     // small problems: fewer, full-length CTAs
+    if (n < 1) n = 1;
+    Segments s;
+    s.n_ctas = (int)n; s.base = (int)(total / n); s.rem = (int)(total % n);
+    return s;
+}
+
+inline int& fwd_seg_target() { static int v = 0; return v; }   // tuning: forward segment length in column tiles (0 = default)
+
 // `sms` = multiprocessor count of the current device (148 on B200).
 inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int sms) {
     if (b_loc < 1 || b_glob < 1 || d < 1 || d > 512) return false;
@@ -75,6 +121,10 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.fwd_rows = kFwdWarps * (32 / p.dpt);
     p.n_rb_fwd = p.bl_pad / p.fwd_rows;
     choose_splits(p.n_rb_fwd, sms * 3, p.bg_pad, p.jt, 4, p.n_js_fwd, p.js_len_fwd);   // 3 resident CTAs per SM
+    p.tiles_fwd = p.bg_pad / p.jt;
+    p.seg_fwd = plan_segments(p.n_rb_fwd, p.tiles_fwd, sms * 3, fwd_seg_target() > 0 ? fwd_seg_target() : 21);
+    p.slots_fwd = (p.tiles_fwd - 1) / p.seg_fwd.base + 2;
+    if (p.slots_fwd > kMaxSplits) p.slots_fwd = kMaxSplits;
     // ---- fused backward sweep: its launcher plans the column split for the CTA shape it runs (<= kMaxSplits)
     p.sms = sms;
 
@@ -92,7 +142,9 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.off_J2 = off;    off = align256(off + (size_t)p.bl_pad * sizeof(float));
     p.ld_s2 = p.bg_pad;
     p.off_s2 = off;    off = align256(off + (p.save ? (size_t)p.bl_pad * p.ld_s2 * sizeof(float) : 0));
-    const size_t fwd_scratch = (size_t)p.n_js_fwd * row_arr + (size_t)p.n_js_fwd * p.bl_pad * 2 * sizeof(float);
+    const int n_part = p.n_js_fwd > p.slots_fwd ? p.n_js_fwd : p.slots_fwd;
+    p.n_part_fwd = n_part;
+    const size_t fwd_scratch = (size_t)n_part * row_arr + (size_t)n_part * p.bl_pad * 2 * sizeof(float);
     p.off_scratch = off; off = align256(off + fwd_scratch);
     p.total_bytes = off;
 

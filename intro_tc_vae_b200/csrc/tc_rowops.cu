@@ -52,6 +52,7 @@ __global__ void reparam_fwd_kernel(const float* __restrict__ mu, int64_t ldmu, c
     }
 }
 
+template <bool ACC>     // ACC: add to grad_mu / grad_logvar (they already hold the gradients of the loss terms that read mu, logvar)
 __global__ void reparam_bwd_kernel(const float* __restrict__ lv, int64_t ldlv, const float* __restrict__ eps, int64_t ldeps,
                                    const float* __restrict__ gz, int64_t ldgz, int b, int d,
                                    float* __restrict__ gmu, int64_t ldgmu, float* __restrict__ glv, int64_t ldglv) {
@@ -60,8 +61,9 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ lv, int64_t ldlv, c
         const int i = (int)(idx / d), dd = (int)(idx % d);
         const float g = gz[(int64_t)i * ldgz + dd];
         const float std = expf(0.5f * lv[(int64_t)i * ldlv + dd]);
-        gmu[(int64_t)i * ldgmu + dd] = g;
-        glv[(int64_t)i * ldglv + dd] = g * eps[(int64_t)i * ldeps + dd] * (0.5f * std);
+        const float dl = g * eps[(int64_t)i * ldeps + dd] * (0.5f * std);
+        if (ACC) { gmu[(int64_t)i * ldgmu + dd] += g; glv[(int64_t)i * ldglv + dd] += dl; }
+        else     { gmu[(int64_t)i * ldgmu + dd] = g;  glv[(int64_t)i * ldglv + dd] = dl; }
     }
 }
 
@@ -252,9 +254,10 @@ cudaError_t launch_reparam_fwd(const float* mu, int64_t ldmu, const float* lv, i
     return cudaGetLastError();
 }
 cudaError_t launch_reparam_bwd(const float* lv, int64_t ldlv, const float* eps, int64_t ldeps, const float* gz, int64_t ldgz,
-                               int b, int d, float* gmu, int64_t ldgmu, float* glv, int64_t ldglv, cudaStream_t st) {
+                               int b, int d, float* gmu, int64_t ldgmu, float* glv, int64_t ldglv, bool accumulate, cudaStream_t st) {
     LaunchScope scope(kKernNone, st);
-    reparam_bwd_kernel<<<grid1d((int64_t)b * d, 256), 256, 0, st>>>(lv, ldlv, eps, ldeps, gz, ldgz, b, d, gmu, ldgmu, glv, ldglv);
+    if (accumulate) reparam_bwd_kernel<true><<<grid1d((int64_t)b * d, 256), 256, 0, st>>>(lv, ldlv, eps, ldeps, gz, ldgz, b, d, gmu, ldgmu, glv, ldglv);
+    else            reparam_bwd_kernel<false><<<grid1d((int64_t)b * d, 256), 256, 0, st>>>(lv, ldlv, eps, ldeps, gz, ldgz, b, d, gmu, ldgmu, glv, ldglv);
     return cudaGetLastError();
 }
 cudaError_t launch_rowdensity_fwd(const float* x, int64_t ldx, const float* mu, int64_t ldmu, const float* lv, int64_t ldlv,

@@ -9,7 +9,7 @@ cudaError_t launch_kl_bwd(const float* lv, int64_t ldlv, const float* mu, int64_
 cudaError_t launch_reparam_fwd(const float* mu, int64_t ldmu, const float* lv, int64_t ldlv, const float* eps, int64_t ldeps,
                                int b, int d, float* z, int64_t ldz, cudaStream_t st);
 cudaError_t launch_reparam_bwd(const float* lv, int64_t ldlv, const float* eps, int64_t ldeps, const float* gz, int64_t ldgz,
-                               int b, int d, float* gmu, int64_t ldgmu, float* glv, int64_t ldglv, cudaStream_t st);
+                               int b, int d, float* gmu, int64_t ldgmu, float* glv, int64_t ldglv, bool accumulate, cudaStream_t st);
 cudaError_t launch_rowdensity_fwd(const float* x, int64_t ldx, const float* mu, int64_t ldmu, const float* lv, int64_t ldlv,
                                   int b, int d, float* out, cudaStream_t st);
 cudaError_t launch_rowdensity_bwd(const float* x, int64_t ldx, const float* mu, int64_t ldmu, const float* lv, int64_t ldlv,

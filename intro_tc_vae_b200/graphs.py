@@ -1,9 +1,9 @@
 """CUDA-graph capture of one TC-ELBO loss evaluation (forward + backward) for fixed shapes.
 
-A row-sharded step at 8 GPUs is ~1 ms of kernels behind ~10 launches and two NCCL collectives, which
-eager PyTorch cannot issue fast enough from one Python thread; replaying a captured graph removes the
-launch gaps.  Everything the library launches is capturable by construction (no host synchronisation,
-no allocation inside the C ABI, explicit stream argument)."""
+A row-sharded step at 8 GPUs is ~1 ms of kernels behind ~10 launches and two exchange steps, which eager
+PyTorch cannot issue fast enough from one Python thread; replaying a captured graph removes the launch gaps.
+Everything the library launches is capturable by construction (no host synchronisation, no allocation inside
+the C ABI, explicit stream argument)."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 from torch import Tensor
 
-from . import ops
+from . import _lib, ops
 
 
 class GraphedKLLoss:
@@ -23,20 +23,32 @@ class GraphedKLLoss:
     evaluated and differentiated inside one CUDA graph.  ``mu``/``logvar``/``eps`` are ``[b_loc, d]`` fp32 CUDA
     tensors (or pinned host tensors: they are copied into the graph's static inputs on the current stream);
     the returned tensors are the graph's static outputs and are overwritten by the next call.
-    ``group``: row-shard over the ranks of a process group (NCCL all-gather / reduce-scatter are captured too).
-    ``exchange="peer"``: do the two exchange steps over NVLink peer memory inside the library's kernels
-    (:mod:`intro_tc_vae_b200.peer`) instead of NCCL; ``"nccl"`` keeps the collectives; ``"auto"`` picks peer memory
-    when the group has more than one rank and symmetric memory can be set up, NCCL otherwise.
+
+    ``group``: row-shard over the ranks of a process group; ``loss`` is then the mean over this rank's rows.
+    ``exchange``: how the column operand and its gradient cross ranks -- ``"nccl"`` (all-gather / reduce-scatter,
+    captured in the graph), ``"peer"`` (the library's own kernels over NVLink peer memory,
+    :mod:`intro_tc_vae_b200.peer`), or ``"auto"`` (peer memory when it can be set up, NCCL otherwise).
+    ``mode``: ``"direct"`` drives the C ABI itself (reparameterize -> fused loss forward -> fused loss backward ->
+    reparameterize backward, 10 launches); ``"autograd"`` records the same step through ``torch.autograd`` (the
+    public ops plus autograd's fill / accumulate kernels) and exists to cross-check the direct path.
     """
 
     def __init__(self, b_loc: int, d: int, dataset_size: int, beta: float, device, group=None,
-                 estimator: str = "mss", warmup: int = 3, exchange: str = "nccl"):
+                 estimator: str = "mss", warmup: int = 3, exchange: str = "nccl", mode: str = "direct"):
+        if mode not in ("direct", "autograd"):
+            raise ValueError(f"mode must be 'direct' or 'autograd', got {mode!r}")
+        if estimator not in ("mss", "mws"):
+            raise ValueError(f"estimator must be 'mss' or 'mws', got {estimator!r}")
         self.device = torch.device(device)
+        self.mode = mode
+        self.group = group
+        self.world, self.rank = 1, 0
         self.exchange = None
         self.exchange_kind = "none"
         if group is not None:
             import torch.distributed as dist
-            if dist.get_world_size(group) > 1:
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            if self.world > 1:
                 self.exchange_kind = "nccl"
                 if exchange not in ("nccl", "peer", "auto"):
                     raise ValueError(f"exchange must be 'nccl', 'peer' or 'auto', got {exchange!r}")
@@ -48,29 +60,39 @@ class GraphedKLLoss:
                     except Exception:
                         if exchange == "peer":
                             raise
-        self.mu = torch.zeros(b_loc, d, device=self.device, requires_grad=True)
-        self.logvar = torch.zeros(b_loc, d, device=self.device, requires_grad=True)
+        self.b_loc, self.d = int(b_loc), int(d)
+        self.mu = torch.zeros(b_loc, d, device=self.device, requires_grad=(mode == "autograd"))
+        self.logvar = torch.zeros(b_loc, d, device=self.device, requires_grad=(mode == "autograd"))
         self.eps = torch.zeros(b_loc, d, device=self.device)
         self._args = (int(dataset_size), float(beta), estimator, group)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss: Optional[Tensor] = None
+        self.dmu: Optional[Tensor] = None
+        self.dlogvar: Optional[Tensor] = None
         with torch.no_grad():                              # benign values for the warm-up / capture passes
             self.logvar.fill_(-2.0)
+        if mode == "direct":
+            self._alloc_direct()
+        step = self._direct_step if mode == "direct" else self._autograd_step
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):
-                self._eager_step()
+                step()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
-        self.mu.grad = None
-        self.logvar.grad = None
+        if mode == "autograd":
+            self.mu.grad = None
+            self.logvar.grad = None
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.loss = self._eager_step()
+            self.loss = step()
         self.graph = graph
+        if mode == "autograd":
+            self.dmu, self.dlogvar = self.mu.grad, self.logvar.grad
 
-    def _eager_step(self) -> Tensor:
+    # ---- the step through torch.autograd -------------------------------------------------------------
+    def _autograd_step(self) -> Tensor:
         n, beta, estimator, group = self._args
         self.mu.grad = None
         self.logvar.grad = None
@@ -79,15 +101,92 @@ class GraphedKLLoss:
         loss.backward()
         return loss.detach()
 
+    # ---- the same step driven through the C ABI ------------------------------------------------------
+    def _alloc_direct(self) -> None:
+        lib = _lib.load()
+        n, beta, estimator, _ = self._args
+        dev, b_loc, d = self.device, self.b_loc, self.d
+        self._flags = (_lib.EST_MSS if estimator == "mss" else _lib.EST_MWS) | _lib.VAR_ROW | _lib.SAVE_FOR_BACKWARD
+        b_glob = b_loc * self.world
+        if estimator == "mss" and b_glob == 1:
+            raise ZeroDivisionError("float division by zero")       # ops.py:44 with M = B-1 = 0
+        ws_bytes = lib.tcelbo_workspace_bytes(b_loc, b_glob, d, self._flags)
+        sc_bytes = lib.tcelbo_backward_scratch_bytes(b_loc, b_glob, d, self._flags)
+        if ws_bytes == 0 or sc_bytes == 0:
+            raise NotImplementedError(f"tcelbo: unsupported shape b_loc={b_loc} b_glob={b_glob} d={d} (d must be <= 512)")
+        f32 = dict(dtype=torch.float32, device=dev)
+        self._z = torch.empty(b_loc, d, **f32)
+        self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        self._scratch = None if self.exchange is not None else torch.empty(sc_bytes, dtype=torch.uint8, device=dev)
+        self._sc_bytes = sc_bytes
+        self._rows = [torch.empty(b_loc, **f32) for _ in range(4)]        # loss, kl, log_qz, log_qz_prod
+        self._g_loss = torch.full((b_loc,), 1.0 / b_loc, **f32)           # d mean / d loss_i
+        self._gz = torch.empty(b_loc, d, **f32)
+        self.dmu = torch.empty(b_loc, d, **f32)
+        self.dlogvar = torch.empty(b_loc, d, **f32)
+        nccl = self.world > 1 and self.exchange is None
+        self._mu_all = torch.empty(b_glob, d, **f32) if nccl else None
+        self._gmu_all = torch.empty(b_glob, d, **f32) if nccl else None
+
+    def _direct_step(self) -> Tensor:
+        import torch.distributed as dist
+        lib = _lib.load()
+        n, beta, _, group = self._args
+        b_loc, d, flags = self.b_loc, self.d, self._flags
+        mu, lv, eps, z = self.mu, self.logvar, self.eps, self._z
+        P = lambda t: t.data_ptr()                                       # noqa: E731
+        rows = [P(t) for t in self._rows]
+        exch = self.exchange
+        with torch.cuda.device(self.device), torch.no_grad():
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(lib.tcelbo_reparam_forward(P(mu), d, P(lv), d, P(eps), d, b_loc, d, P(z), d, st), "tcelbo_reparam_forward")
+            if exch is not None:
+                k = exch.next_forward()
+                exch.mu_sym[k].copy_(mu)
+                exch.mu_hdl.barrier(channel=0)
+                _lib.check(lib.tcelbo_klloss_forward_peer(P(z), d, P(mu), d, P(exch.mu_tables[k]), d, P(lv), d, b_loc, self.world,
+                                                          self.rank, d, n, flags, beta, *rows, P(self._ws), self._ws.numel(), st),
+                           "tcelbo_klloss_forward_peer")
+            else:
+                mu_all, row_offset = mu, 0
+                if self._mu_all is not None:
+                    dist.all_gather_into_tensor(self._mu_all, mu, group=group)
+                    mu_all, row_offset = self._mu_all, self.rank * b_loc
+                _lib.check(lib.tcelbo_klloss_forward(P(z), d, P(mu_all), d, P(lv), d, b_loc, mu_all.shape[0], row_offset, d, n, flags,
+                                                     beta, *rows, P(self._ws), self._ws.numel(), st), "tcelbo_klloss_forward")
+            loss = self._rows[0].mean()
+            if exch is not None:
+                k = exch.next_backward()
+                scratch = exch.scratch_sym[k]
+                for phase in (_lib.PEER_SWEEP, _lib.PEER_FINISH):
+                    _lib.check(lib.tcelbo_klloss_backward_peer(phase, P(z), d, P(mu), d, P(lv), d, b_loc, self.world, self.rank, d, n,
+                                                               flags, beta, P(self._g_loss), None, None, None,
+                                                               P(self._gz), d, P(self.dmu), d, P(self.dlogvar), d,
+                                                               P(self._ws), self._ws.numel(), P(scratch), exch.scratch_bytes,
+                                                               P(exch.scratch_tables[k]), st), "tcelbo_klloss_backward_peer")
+                    if phase == _lib.PEER_SWEEP:
+                        exch.scratch_hdl.barrier(channel=0)
+            else:
+                gmu = self._gmu_all if self._gmu_all is not None else self.dmu
+                _lib.check(lib.tcelbo_klloss_backward(P(z), d, P(mu_all), d, P(lv), d, b_loc, mu_all.shape[0], row_offset, d, n, flags,
+                                                      beta, P(self._g_loss), None, None, None, P(self._gz), d, P(gmu), d,
+                                                      P(self.dlogvar), d, P(self._ws), self._ws.numel(),
+                                                      P(self._scratch), self._sc_bytes, st), "tcelbo_klloss_backward")
+                if self._gmu_all is not None:
+                    dist.reduce_scatter_tensor(self.dmu, self._gmu_all, op=dist.ReduceOp.SUM, group=group)
+            _lib.check(lib.tcelbo_reparam_backward_acc(P(lv), d, P(eps), d, P(self._gz), d, b_loc, d, P(self.dmu), d,
+                                                       P(self.dlogvar), d, st), "tcelbo_reparam_backward_acc")
+        return loss
+
     def __call__(self, mu: Tensor, logvar: Tensor, eps: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         with torch.no_grad():
             self.mu.copy_(mu, non_blocking=True)
             self.logvar.copy_(logvar, non_blocking=True)
             self.eps.copy_(eps, non_blocking=True)
         self.graph.replay()
-        return self.loss, self.mu.grad, self.logvar.grad
+        return self.loss, self.dmu, self.dlogvar
 
     def replay(self) -> Tuple[Tensor, Tensor, Tensor]:
         """Re-run on the inputs already resident in the static buffers."""
         self.graph.replay()
-        return self.loss, self.mu.grad, self.logvar.grad
+        return self.loss, self.dmu, self.dlogvar

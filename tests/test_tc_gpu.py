@@ -544,3 +544,36 @@ def test_reconstruction_loss_and_exp_elbo_against_torch(loss_type, shape):
     assert relerr(outs[1][2], outs[0][2]) < LOSS_RTOL
     assert relerr(outs[1][3], outs[0][3]) < GRAD_RTOL
     assert relerr(outs[1][4], outs[0][4]) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("B,D,family,estimator", [(256, 128, "base", "mss"), (1000, 64, "sharp", "mss"), (384, 20, "base", "mws")])
+def test_graphed_step_matches_eager_autograd_and_oracle(B, D, family, estimator):
+    """GraphedKLLoss (direct C-ABI step and autograd-recorded step, both replayed from a CUDA graph, fresh inputs on every
+    replay) == the eager public ops == the CPU oracle's reparameterize -> compute_kl_loss -> mean -> backward."""
+    from intro_tc_vae_b200.graphs import GraphedKLLoss
+    ops = _ops()
+    N, beta = 16704, 0.5
+    g_direct = GraphedKLLoss(B, D, N, beta, "cuda:0", estimator=estimator, mode="direct")
+    g_auto = GraphedKLLoss(B, D, N, beta, "cuda:0", estimator=estimator, mode="autograd")
+    for seed in (5, 6):
+        mu_c, lv_c, eps_c = _random_latents(B, D, family, seed=seed)
+        mu = mu_c.cuda().requires_grad_(True)
+        lv = lv_c.cuda().requires_grad_(True)
+        z = ops.reparameterize(mu, lv, eps_c.cuda())
+        loss = ops.kl_tc_loss_terms(z, mu, lv, N, beta, estimator)[0].mean()
+        loss.backward()
+        for graphed in (g_direct, g_auto):
+            l, dmu, dlv = graphed(mu_c.cuda(), lv_c.cuda(), eps_c.cuda())
+            assert relerr(l.reshape(1), loss.detach().reshape(1)) < 2e-6
+            assert relerr(dmu, mu.grad) < 1e-5
+            assert relerr(dlv, lv.grad) < 1e-5
+        if estimator == "mss":
+            mu_o = mu_c.clone().requires_grad_(True)
+            lv_o = lv_c.clone().requires_grad_(True)
+            z_o = O.reparameterize(mu_o, lv_o, eps_c)
+            loss_o = ((beta - 1.0) * O.total_correlation(z_o, mu_o, lv_o, N, reduce="none") + O.kl_divergence(lv_o, mu_o, reduce="none")).mean()
+            loss_o.backward()
+            l, dmu, dlv = g_direct(mu_c.cuda(), lv_c.cuda(), eps_c.cuda())
+            assert relerr(l.reshape(1), loss_o.detach().reshape(1)) < LOSS_RTOL
+            assert relerr(dmu, mu_o.grad) < GRAD_RTOL
+            assert relerr(dlv, lv_o.grad) < GRAD_RTOL

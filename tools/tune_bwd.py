@@ -17,6 +17,9 @@ def main():
     ap.add_argument("--zdim", type=int, default=128)
     ap.add_argument("--variants", default="-1,0,1,2,4,11,30,20,21,22")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--rows", type=int, default=0, help="rows of this shard (default: the whole batch); emulates one rank of a row-sharded job")
+    ap.add_argument("--fwd-seg", default="", help="comma list of forward segment-length targets (column tiles per CTA)")
+    ap.add_argument("--seg", default="0", help="comma list of segment-length targets (column tiles per CTA; 0 = default)")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda:0")
@@ -25,14 +28,17 @@ def main():
     mu = torch.randn(B, D, generator=g).to(dev)
     lv = (-2.0 + torch.randn(B, D, generator=g)).to(dev)
     z = mu + torch.randn(B, D, generator=g).to(dev) * torch.exp(0.5 * lv)
+    R = args.rows if args.rows > 0 else B
+    z, lv = z[:R].contiguous(), lv[:R].contiguous()
     flags = _lib.EST_MSS | _lib.VAR_ROW | _lib.SAVE_FOR_BACKWARD
     lq, lqp, ws = torch.ops.tcelbo.tc_forward(z, mu, lv, 0, N, flags)
-    gj = torch.full((B,), 0.5 / B, device=dev)
+    gj = torch.full((R,), 0.5 / B, device=dev)
     gp = -gj
     ref = None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    for v in [int(x) for x in args.variants.split(",")]:
+    for v, seg in [(int(x), int(y)) for x in args.variants.split(",") for y in args.seg.split(",")]:
         _lib.check(lib.tcelbo_set_tuning(b"bwd_variant", v), "set_tuning")
+        _lib.check(lib.tcelbo_set_tuning(b"bwd_seg_tiles", seg), "set_tuning")
         try:
             for _ in range(2):
                 out = torch.ops.tcelbo.tc_backward(z, mu, lv, 0, N, flags, gj, gp, ws)
@@ -55,8 +61,30 @@ def main():
         else:
             err = max(((a - b).abs().max() / b.abs().max()).item() for a, b in zip(out, ref))
         ts.sort()
-        print(f"variant {v:2d}: backward total {ts[len(ts)//2]:.3f} ms (min {ts[0]:.3f})  max rel diff vs first {err:.1e}")
+        print(f"variant {v:2d} seg {seg:3d}: backward total {ts[len(ts)//2]:.3f} ms (min {ts[0]:.3f})  max rel diff vs first {err:.1e}")
     lib.tcelbo_set_tuning(b"bwd_variant", -1)
+    lib.tcelbo_set_tuning(b"bwd_seg_tiles", 0)
+    # forward sweep: segment-length targets
+    ref = None
+    for seg in [int(y) for y in args.fwd_seg.split(",") if y]:
+        _lib.check(lib.tcelbo_set_tuning(b"fwd_seg_tiles", seg), "set_tuning")
+        for _ in range(2):
+            out = torch.ops.tcelbo.tc_forward(z, mu, lv, 0, N, flags)
+        ts = []
+        for _ in range(args.reps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = torch.ops.tcelbo.tc_forward(z, mu, lv, 0, N, flags)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        if ref is None:
+            ref = [t.clone() for t in out[:2]]
+        err = max(((a - b).abs().max() / b.abs().max()).item() for a, b in zip(out[:2], ref))
+        ts.sort()
+        print(f"forward seg {seg:3d}: forward total {ts[len(ts)//2]:.3f} ms (min {ts[0]:.3f})  max rel diff vs first {err:.1e}")
+    lib.tcelbo_set_tuning(b"fwd_seg_tiles", 0)
 
 
 if __name__ == "__main__":
