@@ -213,20 +213,20 @@ def run_ours(args):
     graphed = None
     graph_note = "eager"
     exchange_note = "nccl" if world > 1 else "none"
-    if not args.no_graph:
-        try:
-            from intro_tc_vae_b200.graphs import GraphedKLLoss
-            graphed = GraphedKLLoss(b_loc, D, N, BETA, dev, group=group, exchange=args.exchange)
-            exchange_note = graphed.exchange_kind
-            graphed(mu.detach(), lv.detach(), eps)
-            torch.cuda.synchronize()
-            ref_loss = step(mu, lv, eps).item()
-            got = graphed.loss.item()
-            assert abs(got - ref_loss) <= 1e-5 * abs(ref_loss), (got, ref_loss)
-            graph_note = "cuda-graph replay of the whole step (reparameterize + fused loss forward + backward)"
-        except Exception as exc:                           # capture unsupported here: fall back to eager launches
-            graphed = None
-            graph_note = f"eager (graph capture failed: {type(exc).__name__}: {exc})"[:200]
+    try:
+        from intro_tc_vae_b200.graphs import GraphedKLLoss
+        graphed = GraphedKLLoss(b_loc, D, N, BETA, dev, group=group, exchange=args.exchange, capture=not args.no_graph)
+        exchange_note = graphed.exchange_kind
+        graphed(mu.detach(), lv.detach(), eps)
+        torch.cuda.synchronize()
+        ref_loss = step(mu, lv, eps).item()
+        got = graphed.loss.item()
+        assert abs(got - ref_loss) <= 1e-5 * abs(ref_loss), (got, ref_loss)
+        graph_note = ("cuda-graph replay of" if not args.no_graph else "eager launches of") + \
+            " the whole step through the C ABI (reparameterize + fused loss forward + backward + reparameterize backward)"
+    except Exception as exc:                           # capture unsupported here: fall back to eager launches
+        graphed = None
+        graph_note = f"eager (graph capture failed: {type(exc).__name__}: {exc})"[:200]
     ok = torch.tensor([1 if graphed is not None else 0], device=dev)
     if world > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)

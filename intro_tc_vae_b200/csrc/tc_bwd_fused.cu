@@ -469,16 +469,16 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
             // partial slots of this (slice, row block): one per segment that touches the block
             const int64_t qb = (int64_t)(dd / a.slice_dp) * a.n_rb + i / a.rows_per_block;
             const int n_slots = seg_slots(a.seg, qb, a.tiles_per_block);
-            for (int s0 = 0; s0 < n_slots; s0 += 8) {
-                float va[8], vc[8];
+            for (int s0 = 0; s0 < n_slots; s0 += 4) {
+                float va[4], vc[4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 4; ++k) {
                     const bool ok = s0 + k < n_slots;
                     va[k] = ok ? __ldg(a.Apart + (size_t)(s0 + k) * split_stride + o) : 0.0f;
                     vc[k] = ok ? __ldg(a.CRpart + (size_t)(s0 + k) * split_stride + o) : 0.0f;
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { sa += va[k]; sc += vc[k]; }
+                for (int k = 0; k < 4; ++k) { sa += va[k]; sc += vc[k]; }
             }
             float glv = a.vr[o] * sc;
             if (a.gk != nullptr) glv += a.gk[i] * 0.5f * (expf(a.lv[(int64_t)i * a.ldlv + dd]) - 1.0f);

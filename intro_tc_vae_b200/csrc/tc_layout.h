@@ -34,7 +34,9 @@ TCELBO_HD inline int64_t seg_begin(const Segments& s, int c) { return (int64_t)c
 TCELBO_HD inline int seg_len(const Segments& s, int c) { return s.base + (c < s.rem ? 1 : 0); }
 TCELBO_HD inline int seg_of(const Segments& s, int64_t g) {           // the segment that holds tile g
     const int64_t cut = (int64_t)s.rem * (s.base + 1);
-    return g < cut ? (int)(g / (s.base + 1)) : s.rem + (int)((g - cut) / s.base);
+    if (g < cut) return g <= 0x7fffffff ? (int)((uint32_t)g / (uint32_t)(s.base + 1)) : (int)(g / (s.base + 1));
+    const int64_t h = g - cut;
+    return s.rem + (h <= 0x7fffffff ? (int)((uint32_t)h / (uint32_t)s.base) : (int)(h / s.base));
 }
 // number of segments that touch block q (tiles [q*T, (q+1)*T))
 TCELBO_HD inline int seg_slots(const Segments& s, int64_t q, int tiles_per_block) {

@@ -31,10 +31,12 @@ class GraphedKLLoss:
     ``mode``: ``"direct"`` drives the C ABI itself (reparameterize -> fused loss forward -> fused loss backward ->
     reparameterize backward, 10 launches); ``"autograd"`` records the same step through ``torch.autograd`` (the
     public ops plus autograd's fill / accumulate kernels) and exists to cross-check the direct path.
+    ``capture=False`` issues the same launches eagerly on every call instead of replaying a graph (for profilers that
+    want to see individual launches).
     """
 
     def __init__(self, b_loc: int, d: int, dataset_size: int, beta: float, device, group=None,
-                 estimator: str = "mss", warmup: int = 3, exchange: str = "nccl", mode: str = "direct"):
+                 estimator: str = "mss", warmup: int = 3, exchange: str = "nccl", mode: str = "direct", capture: bool = True):
         if mode not in ("direct", "autograd"):
             raise ValueError(f"mode must be 'direct' or 'autograd', got {mode!r}")
         if estimator not in ("mss", "mws"):
@@ -84,10 +86,14 @@ class GraphedKLLoss:
         if mode == "autograd":
             self.mu.grad = None
             self.logvar.grad = None
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        self._step = step
+        if capture:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.loss = step()
+            self.graph = graph
+        else:
             self.loss = step()
-        self.graph = graph
         if mode == "autograd":
             self.dmu, self.dlogvar = self.mu.grad, self.logvar.grad
 
@@ -183,10 +189,14 @@ class GraphedKLLoss:
             self.mu.copy_(mu, non_blocking=True)
             self.logvar.copy_(logvar, non_blocking=True)
             self.eps.copy_(eps, non_blocking=True)
-        self.graph.replay()
-        return self.loss, self.dmu, self.dlogvar
+        return self.replay()
 
     def replay(self) -> Tuple[Tensor, Tensor, Tensor]:
         """Re-run on the inputs already resident in the static buffers."""
-        self.graph.replay()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.loss = self._step()
+            if self.mode == "autograd":
+                self.dmu, self.dlogvar = self.mu.grad, self.logvar.grad
         return self.loss, self.dmu, self.dlogvar

@@ -577,3 +577,62 @@ def test_graphed_step_matches_eager_autograd_and_oracle(B, D, family, estimator)
             assert relerr(l.reshape(1), loss_o.detach().reshape(1)) < LOSS_RTOL
             assert relerr(dmu, mu_o.grad) < GRAD_RTOL
             assert relerr(dlv, lv_o.grad) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("B,D,parts,family", [(256, 128, 2, "base"), (384, 64, 4, "sharp"), (296, 20, 8, "base"), (512, 256, 2, "base")])
+def test_peer_exchange_entry_points_emulated_on_one_gpu(B, D, parts, family):
+    """tcelbo_klloss_forward_peer / _backward_peer take plain device pointer tables, so P ranks can be played one after the
+    other on one GPU: every rank's column gather reads all P row blocks, every rank's finish sums its rows over all P scratch
+    buffers.  Must equal the single-shard fused loss (values, grad_z, grad_logvar and the reduce-scattered grad_mu)."""
+    from intro_tc_vae_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    N, beta = 16704, 2.5
+    mu_c, lv_c, eps_c = _random_latents(B, D, family, seed=77)
+    mu, lv = mu_c.to(dev), lv_c.to(dev)
+    z = ops.reparameterize(mu, lv, eps_c.to(dev))
+    g = [torch.linspace(0.3, 1.1, B, device=dev), torch.linspace(-0.4, 0.6, B, device=dev),
+         torch.linspace(0.9, -0.2, B, device=dev), torch.linspace(0.1, 0.5, B, device=dev)]
+    # single-shard reference through the public op
+    mu_r, lv_r, z_r = mu.clone().requires_grad_(True), lv.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    outs_r = ops.kl_tc_loss_terms(z_r, mu_r, lv_r, N, beta)
+    sum((o * w).sum() for o, w in zip(outs_r, g)).backward()
+
+    b_loc = B // parts
+    flags = _lib.EST_MSS | _lib.VAR_ROW | _lib.SAVE_FOR_BACKWARD
+    ws_bytes = lib.tcelbo_workspace_bytes(b_loc, B, D, flags)
+    sc_bytes = lib.tcelbo_backward_scratch_bytes(b_loc, B, D, flags)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    P = lambda t: t.data_ptr()                                       # noqa: E731
+    shards = [slice(r * b_loc, (r + 1) * b_loc) for r in range(parts)]
+    mu_parts = [mu[s].contiguous() for s in shards]                  # one allocation per "rank"
+    mu_table = torch.tensor([P(t) for t in mu_parts], dtype=torch.int64, device=dev)
+    ws = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(parts)]
+    scratch = [torch.empty(sc_bytes, dtype=torch.uint8, device=dev) for _ in range(parts)]
+    sc_table = torch.tensor([P(t) for t in scratch], dtype=torch.int64, device=dev)
+    rows = [[torch.empty(b_loc, device=dev) for _ in range(4)] for _ in range(parts)]
+    zs, lvs = [z[s].contiguous() for s in shards], [lv[s].contiguous() for s in shards]
+    for r in range(parts):
+        _lib.check(lib.tcelbo_klloss_forward_peer(P(zs[r]), D, P(mu_parts[r]), D, P(mu_table), D, P(lvs[r]), D, b_loc, parts, r, D, N,
+                                                  flags, beta, *[P(t) for t in rows[r]], P(ws[r]), ws_bytes, st), "forward_peer")
+    for k in range(4):
+        assert relerr(torch.cat([rows[r][k] for r in range(parts)]), outs_r[k]) < 2e-6
+    gs = [[w[s].contiguous() for w in g] for s in shards]
+    gz = [torch.empty(b_loc, D, device=dev) for _ in range(parts)]
+    gmu = [torch.empty(b_loc, D, device=dev) for _ in range(parts)]
+    glv = [torch.empty(b_loc, D, device=dev) for _ in range(parts)]
+    for phase in (_lib.PEER_SWEEP, _lib.PEER_FINISH):                # all sweeps, then ("after the barrier") all finishes
+        for r in range(parts):
+            _lib.check(lib.tcelbo_klloss_backward_peer(phase, P(zs[r]), D, P(mu_parts[r]), D, P(lvs[r]), D, b_loc, parts, r, D, N, flags,
+                                                       beta, *[P(t) for t in gs[r]], P(gz[r]), D, P(gmu[r]), D, P(glv[r]), D,
+                                                       P(ws[r]), ws_bytes, P(scratch[r]), sc_bytes, P(sc_table), st), "backward_peer")
+    assert relerr(torch.cat(gz), z_r.grad) < 1e-5
+    assert relerr(torch.cat(glv), lv_r.grad) < 1e-5
+    assert relerr(torch.cat(gmu), mu_r.grad) < 1e-5
+    # argument validation
+    assert lib.tcelbo_klloss_backward_peer(3, P(zs[0]), D, P(mu_parts[0]), D, P(lvs[0]), D, b_loc, parts, 0, D, N, flags, beta,
+                                           *[P(t) for t in gs[0]], P(gz[0]), D, P(gmu[0]), D, P(glv[0]), D, P(ws[0]), ws_bytes,
+                                           P(scratch[0]), sc_bytes, P(sc_table), st) != 0
+    assert lib.tcelbo_klloss_forward_peer(P(zs[0]), D, P(mu_parts[0]), D, P(mu_table), D, P(lvs[0]), D, b_loc, parts, parts, D, N,
+                                          flags, beta, *[P(t) for t in rows[0]], P(ws[0]), ws_bytes, st) != 0
