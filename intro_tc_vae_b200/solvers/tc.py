@@ -18,6 +18,8 @@ from .vae import VAESolver
 
 class TCLossMixin:
     process_group = None          # set to a torch.distributed group to row-shard the estimator
+    peer_exchange = None          # optionally a peer.PeerExchange for that group and shard shape: the all-gather /
+                                  # reduce-scatter of the simple path then run inside the library's kernels over NVLink
 
     def compute_kl_loss(self, z: Optional[Tensor], mu: Tensor, logvar: Tensor, reduce: str = "mean",
                         beta: float = None, write: bool = False) -> Tensor:
@@ -31,7 +33,10 @@ class TCLossMixin:
             beta = self.beta_kl
         dataset_size = len(self.dataset)
         # one fused op: per-sample (beta-1)*tc_i + kl_i and kl_i (KL and the combine ride in the TC kernels' epilogues)
-        loss, kl, _, _ = ops.kl_tc_loss_terms(z, mu, logvar, dataset_size, beta, "mss", getattr(self, "process_group", None))
+        exch = getattr(self, "peer_exchange", None)
+        if exch is not None and tuple(z.shape) != (exch.b_loc, exch.d):
+            exch = None                                              # e.g. a ragged last batch: NCCL path
+        loss, kl, _, _ = ops.kl_tc_loss_terms(z, mu, logvar, dataset_size, beta, "mss", getattr(self, "process_group", None), exch)
         if write:                                                    # KL only, as in the reference (solvers/tc.py:87-88)
             kl_loss = kl.sum() if reduce == "sum" else (kl.mean() if reduce == "mean" else kl)
             self.write_scalar(SingletonWriter().cur_iter, "kl_loss_unscaled", kl_loss)

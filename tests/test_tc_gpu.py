@@ -636,3 +636,19 @@ def test_peer_exchange_entry_points_emulated_on_one_gpu(B, D, parts, family):
                                            P(scratch[0]), sc_bytes, P(sc_table), st) != 0
     assert lib.tcelbo_klloss_forward_peer(P(zs[0]), D, P(mu_parts[0]), D, P(mu_table), D, P(lvs[0]), D, b_loc, parts, parts, D, N,
                                           flags, beta, *[P(t) for t in rows[0]], P(ws[0]), ws_bytes, st) != 0
+
+
+def test_two_gpu_sharded_equals_single_when_available():
+    """NCCL-sharded == peer-memory-sharded == single GPU on one global batch (tools/check_sharded.py under torchrun).
+    Needs two visible GPUs; the round-end single-GPU box skips it."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "check_sharded.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MISMATCH" not in out.stdout
