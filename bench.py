@@ -173,6 +173,8 @@ def run_ours(args):
     lib = _lib.load()
 
     B, D, N = args.batch, args.zdim, DATASET_SIZE
+    if N < B - 1:                  # the stratified weights need N >= B-1 (ops.py:46: log of a negative weight is NaN otherwise)
+        N = 4 * B
     assert B % world == 0, "global batch must divide by the number of ranks"
     b_loc = B // world
     lo = rank * b_loc
