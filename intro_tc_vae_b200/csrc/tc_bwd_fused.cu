@@ -55,24 +55,22 @@ __device__ __forceinline__ void bwd_pairs(const u64 (&mu2)[NP], const u64 (&zs2)
                                           u64 (&A2)[NP], u64 (&CR2)[NP], u64 (&G2)[NP]) {
     const u64 gq2 = pack2(gq, gq);
     const u64 rho2 = pack2(rho, rho);
-    const u64 k2 = pack2(kTwoLn2, kTwoLn2);
-    const u64 neg1 = pack2(-1.0f, -1.0f);
+    const u64 nk2 = pack2(-kInvTwoLn2, -kInvTwoLn2);
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         const u64 dl2 = ffma2(mu2[p], ns2[p], zs2[p]);
-        const u64 q2 = fmul2(dl2, dl2);
+        const u64 q2 = ffma2(dl2, dl2, nk2);                                               // q' = q - 1/(2 ln2)
         float q0, q1;
         unpack2(q2, q0, q1);
-        const float c0 = fmin_nan(q0, qmx[2 * p]), c1 = fmin_nan(q1, qmx[2 * p + 1]);
+        const float c0 = fmin_nan(q0, qmx[2 * p]), c1 = fmin_nan(q1, qmx[2 * p + 1]);      // c' = min(q, qmax) - 1/(2 ln2)
         u64 e2 = (ABL == 2) ? pack2(1.0f - c0, 1.0f - c1) : pack2(ex2(-c0), ex2(-c1));     // ABL 2: no MUFU (timing ablation only)
         if (kWeighted) e2 = fmul2(e2, rho2);
-        const u64 coef2 = ffma2(e2, gps2[p], gq2);
+        const u64 coef2 = ffma2(e2, gps2[p], gq2);                                         // gps' carries the 2^(-1/(2 ln2)) of e'
         const u64 m2 = pack2(fset_le(q0, qmx[2 * p]), fset_le(q1, qmx[2 * p + 1]));
         const u64 r2 = fmul2(coef2, m2);
         const u64 t2 = fmul2(r2, dl2);
         A2[p] = fadd2(A2[p], t2);
-        const u64 u2 = ffma2(pack2(c0, c1), k2, neg1);
-        CR2[p] = ffma2(r2, u2, CR2[p]);
+        CR2[p] = ffma2(r2, pack2(c0, c1), CR2[p]);                                         // sum r c' = sum r (2 ln2 c - 1) / (2 ln2)
         G2[p] = ffma2(t2, ns2[p], G2[p]);
     }
 }
@@ -84,13 +82,13 @@ template <bool kWeighted>
 __device__ __forceinline__ void bwd_elem_pred(float mu, float zs, float ns, float qmx, float gps, float gq, float rho,
                                               float& A, float& CR, float& G) {
     const float dl = fmaf(mu, ns, zs);
-    const float q = dl * dl;
+    const float q = fmaf(dl, dl, -kInvTwoLn2);
     const float c = fmin_nan(q, qmx);
     float e = ex2(-c);
     if (kWeighted) e *= rho;
     const float coef = fmaf(e, gps, gq);
     const float t = coef * dl;
-    const float u = fmaf(c, kTwoLn2, -1.0f);
+    const float u = c;
     asm("{\n\t.reg .pred p;\n\t"
         "setp.leu.f32 p, %3, %4;\n\t"                 // unmasked (or NaN: propagate)
         "@p add.f32 %0, %0, %5;\n\t"
@@ -106,21 +104,20 @@ __device__ __forceinline__ void bwd_rows_phased(const u64 (&mu2)[NP], const u64 
                                                 const float (*qmx)[2 * NP], const u64 (*gps2)[NP],
                                                 const float* gq, int gq_stride, const float* rho,
                                                 u64 (*A2)[NP], u64 (*CR2)[NP], u64 (&G2)[NP]) {
-    const u64 k2 = pack2(kTwoLn2, kTwoLn2);
-    const u64 neg1 = pack2(-1.0f, -1.0f);
+    const u64 nk2 = pack2(-kInvTwoLn2, -kInvTwoLn2);
     u64 dl2[RG][NP], e2[RG][NP], m2[RG][NP], u2[RG][NP];
 #pragma unroll
     for (int r = 0; r < RG; ++r) {
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             dl2[r][p] = ffma2(mu2[p], ns2[r][p], zs2[r][p]);
-            const u64 q2 = fmul2(dl2[r][p], dl2[r][p]);
+            const u64 q2 = ffma2(dl2[r][p], dl2[r][p], nk2);
             float q0, q1;
             unpack2(q2, q0, q1);
             const float c0 = fmin_nan(q0, qmx[r][2 * p]), c1 = fmin_nan(q1, qmx[r][2 * p + 1]);
             e2[r][p] = pack2(ex2(-c0), ex2(-c1));
             m2[r][p] = pack2(fset_le(q0, qmx[r][2 * p]), fset_le(q1, qmx[r][2 * p + 1]));
-            u2[r][p] = ffma2(pack2(c0, c1), k2, neg1);
+            u2[r][p] = pack2(c0, c1);
         }
     }
 #pragma unroll
@@ -284,12 +281,14 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
                 VecLd<VEC>::ld(a.ns + base + c * CH + VEC * lane, v);
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) vn[c * VEC + e] = v[e];
+                // The sweep works with q' = q - 1/(2 ln2): then 2 ln2 q - 1 = 2 ln2 q' and the logvar sum needs no extra FFMA;
+                // 2^-q' = 2^-q * exp(1/2); the exp(-1/2) is folded into gps.
                 VecLd<VEC>::ld(a.qmax + base + c * CH + VEC * lane, v);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) vq[c * VEC + e] = v[e];
+                for (int e = 0; e < VEC; ++e) vq[c * VEC + e] = v[e] - kInvTwoLn2;
                 VecLd<VEC>::ld(a.gps + base + c * CH + VEC * lane, v);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) vg[c * VEC + e] = valid ? v[e] : 0.0f;
+                for (int e = 0; e < VEC; ++e) vg[c * VEC + e] = valid ? v[e] * kRsqrtE : 0.0f;
             }
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
@@ -480,7 +479,7 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { sa += va[k]; sc += vc[k]; }
             }
-            float glv = a.vr[o] * sc;
+            float glv = a.vr[o] * (kTwoLn2 * sc);                         // the sweep accumulates sum r (c - 1/(2 ln2))
             if (a.gk != nullptr) glv += a.gk[i] * 0.5f * (expf(a.lv[(int64_t)i * a.ldlv + dd]) - 1.0f);
             a.grad_z[(int64_t)i * a.ldgz + dd] = kTwoLn2 * a.ns[o] * sa;
             a.grad_lv[(int64_t)i * a.ldglv + dd] = glv;

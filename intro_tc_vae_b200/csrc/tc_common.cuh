@@ -15,6 +15,8 @@ typedef unsigned long long u64;
 constexpr float kLog2e   = 1.4426950408889634f;
 constexpr float kLn2     = 0.6931471805599453f;
 constexpr float kTwoLn2  = 1.3862943611198906f;
+constexpr float kInvTwoLn2 = 0.72134752044448170f;     // 1 / (2 ln 2)
+constexpr float kRsqrtE = 0.60653065971263342f;        // 2^(-1/(2 ln 2)) = e^(-1/2)
 constexpr float kLog2Pi  = 1.8378770664093453f;   // log(2*pi)
 constexpr float kVarFloor = 1e-4f;                // eps of gaussian_nll_loss at ops.py:18
 constexpr float kLogpFloor = -50.0f;              // clamp at ops.py:21,29
