@@ -37,12 +37,12 @@ template <> struct VecLd<4> { static __device__ __forceinline__ void ld(const fl
                               static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
                                   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); } };
 
-template <int DPT, int JS_> struct BwdGeom {
+template <int DPT, int JS_, int JTMAX = 16> struct BwdGeom {
     static constexpr int VEC = DPT < 4 ? DPT : 4;
     static constexpr int NCH = DPT / VEC;
     static constexpr int DP = 32 * DPT;
     static constexpr int CH = 32 * VEC;
-    static constexpr int JT = (kTileFloats / DP) > 16 ? 16 : (kTileFloats / DP);      // columns per pipeline stage
+    static constexpr int JT = (kTileFloats / DP) > JTMAX ? JTMAX : (kTileFloats / DP);  // columns per pipeline stage
     static constexpr int JS = JS_ > JT ? JT : JS_;                                     // columns per G staging buffer
     static constexpr int GV = JS >= 4 ? 4 : JS;                                        // columns per gq vector load
     static constexpr int NP = DPT >= 2 ? DPT / 2 : 1;                                  // f32x2 pairs per row
@@ -140,13 +140,13 @@ __device__ __forceinline__ void bwd_rows_phased(const u64 (&mu2)[NP], const u64 
 
 // All JS columns of one staging sub-tile for this warp's RI rows.  Templated on the special-tile case so
 // the GV unrolled columns form ONE basic block and independent (row, column) chains can be interleaved.
-template <int DPT, int RI, int JS_, bool PHASED, bool kSpecial, int ABL = 0, bool SCALAR = false>
+template <int DPT, int RI, int JS_, bool PHASED, bool kSpecial, int ABL = 0, bool SCALAR = false, int JTMAX = 16>
 __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, const float* __restrict__ gq, float* __restrict__ gst,
                                             int sub, int lane, int jt0, int i_glob0, const Weights& w,
-                                            const u64 (&zs2)[RI][BwdGeom<DPT, JS_>::NP], const u64 (&ns2)[RI][BwdGeom<DPT, JS_>::NP],
-                                            const float (&qmx)[RI][2 * BwdGeom<DPT, JS_>::NP], const u64 (&gps2)[RI][BwdGeom<DPT, JS_>::NP],
-                                            u64 (&A2)[RI][BwdGeom<DPT, JS_>::NP], u64 (&CR2)[RI][BwdGeom<DPT, JS_>::NP]) {
-    using GEO = BwdGeom<DPT, JS_>;
+                                            const u64 (&zs2)[RI][BwdGeom<DPT, JS_, JTMAX>::NP], const u64 (&ns2)[RI][BwdGeom<DPT, JS_, JTMAX>::NP],
+                                            const float (&qmx)[RI][2 * BwdGeom<DPT, JS_, JTMAX>::NP], const u64 (&gps2)[RI][BwdGeom<DPT, JS_, JTMAX>::NP],
+                                            u64 (&A2)[RI][BwdGeom<DPT, JS_, JTMAX>::NP], u64 (&CR2)[RI][BwdGeom<DPT, JS_, JTMAX>::NP]) {
+    using GEO = BwdGeom<DPT, JS_, JTMAX>;
     constexpr int VEC = GEO::VEC, NCH = GEO::NCH, DP = GEO::DP, CH = GEO::CH, JT = GEO::JT, JS = GEO::JS, GV = GEO::GV, NP = GEO::NP;
     constexpr int RG = (RI % 2 == 0) ? 2 : 1;
 #pragma unroll 1
@@ -225,10 +225,10 @@ __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, cons
     }
 }
 
-template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF, int ABL, bool SCALAR>
+template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF, int ABL, bool SCALAR, int JTMAX>
 __global__ void __launch_bounds__(NW * 32, MINB)
 tc_bwd_fused_kernel(const BwdFusedArgs a) {
-    using GEO = BwdGeom<DPT, JS_>;
+    using GEO = BwdGeom<DPT, JS_, JTMAX>;
     constexpr int VEC = GEO::VEC, NCH = GEO::NCH, DP = GEO::DP, CH = GEO::CH, JT = GEO::JT, JS = GEO::JS, GV = GEO::GV, NP = GEO::NP;
     constexpr int TILE = JT * DP;
     constexpr int ROWS = NW * RI;
@@ -421,8 +421,8 @@ tc_bwd_fused_kernel(const BwdFusedArgs a) {
             const int b = k % NBUF;
             if (ABL != 1 && k >= NBUF) mbar_wait(&g_empty[b], ((k / NBUF) - 1) & 1);   // everyone finished reducing sub-tile k-NBUF
             float* gst = gstage + (size_t)b * GST + (size_t)warp * JS * DP;
-            if (special) bwd_subtile<DPT, RI, JS_, PHASED, true, ABL, SCALAR>(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
-            else         bwd_subtile<DPT, RI, JS_, PHASED, false, ABL, SCALAR>(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
+            if (special) bwd_subtile<DPT, RI, JS_, PHASED, true, ABL, SCALAR, JTMAX>(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
+            else         bwd_subtile<DPT, RI, JS_, PHASED, false, ABL, SCALAR, JTMAX>(tile, gq, gst, sub, lane, jt0, a.row_offset + row0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
             if (ABL == 1) continue;                                  // timing ablation: no staging hand-off / reduction
             __syncwarp();
             if (lane == 0) mbar_arrive(&g_full[b]);
@@ -502,15 +502,15 @@ void set_bwd_variant(int v) { g_bwd_variant = v; }
 static int g_bwd_seg_target = 0;    // 0: default target segment length (column tiles per CTA)
 void set_bwd_seg_target(int v) { g_bwd_seg_target = v; }
 
-template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF = 2, int ABL = 0, bool SCALAR = false>
+template <int DPT, int RI, int NW, int MINB, int JS_, bool PHASED, int NBUF = 2, int ABL = 0, bool SCALAR = false, int JTMAX = 16>
 static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, BwdFinArgs* fin, cudaStream_t st) {
-    using GEO = BwdGeom<DPT, JS_>;
+    using GEO = BwdGeom<DPT, JS_, JTMAX>;
     constexpr int ROWS = NW * RI;
     const size_t smem = ((size_t)kStages * GEO::JT * GEO::DP + (size_t)kStages * ROWS * GEO::JT + (size_t)NW * RI * GEO::JT
                          + NBUF * (size_t)NW * GEO::JS * GEO::DP) * sizeof(float) + (2 * kStages + 2 * NBUF) * sizeof(uint64_t);
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
-        auto kern = tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR>;
+        auto kern = tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR, JTMAX>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 0;
@@ -521,14 +521,14 @@ static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, BwdFinArgs*
     const int n_rb = (p.bl_pad + ROWS - 1) / ROWS;
     const int n_slices = p.dp / GEO::DP;                                      // 1 unless a wide latent is walked in 128-dim slices
     const int T = p.bg_pad / GEO::JT;
-    const Segments seg = plan_segments((int64_t)n_rb * n_slices, T, p.sms * ctas_per_sm, g_bwd_seg_target > 0 ? g_bwd_seg_target : 64);
+    const Segments seg = plan_segments((int64_t)n_rb * n_slices, T, p.sms * ctas_per_sm, g_bwd_seg_target > 0 ? g_bwd_seg_target : 1024 / GEO::JT);
     a.js_len = 0;
     a.pitch = p.dp;
     a.seg = seg; a.n_blocks = n_rb * n_slices; a.n_rb = n_rb;
     fin->seg = seg; fin->tiles_per_block = T; fin->n_rb = n_rb; fin->rows_per_block = ROWS; fin->slice_dp = GEO::DP;
     if (a.plan_only) return cudaSuccess;
     LaunchScope scope(kKernBwdRow, st);
-    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR><<<seg.n_ctas, NW * 32, smem, st>>>(a);
+    tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR, JTMAX><<<seg.n_ctas, NW * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -543,6 +543,8 @@ cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* f
                 case 2:  return launch_bwd_fused_t<4, 4, 8, 2, 8, false>(p, a, fin, st);             // 4 rows/warp, 2 CTAs/SM (spills)
                 case 4:  return launch_bwd_fused_t<4, 2, 8, 3, 4, false>(p, a, fin, st);             // 2 rows/warp, 3 CTAs/SM
                 case 11: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 3>(p, a, fin, st);          // three staging buffers
+                case 12: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 3, 0, false, 8>(p, a, fin, st);   // three 8-column staging buffers, 8-column tiles
+                case 13: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, false, 8>(p, a, fin, st);   // 8-column tiles only (control for 12)
                 case 30: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, true>(p, a, fin, st); // scalar predicated loop
                 case 20: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 1>(p, a, fin, st);       // ablation: no column-gradient path
                 case 21: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 2>(p, a, fin, st);       // ablation: no MUFU
