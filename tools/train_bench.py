@@ -110,6 +110,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--peer", action="store_true", help="N>1: run the estimator's exchange steps over NVLink peer memory instead of NCCL")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
@@ -127,6 +128,9 @@ def main():
                       beta_kl=0.5, beta_rec=0.75, beta_neg=512.0, gamma_r=1e-8, device=dev, use_amp=False, grad_scaler=None,
                       writer=None, test_iter=1000, clip=100.0)
     solver.process_group = group
+    if group is not None and args.peer:
+        from intro_tc_vae_b200.peer import PeerExchange
+        solver.peer_exchange = PeerExchange(args.batch, args.zdim, group, dev)
     batch = torch.rand(args.batch, 3, args.image, args.image, device=dev)
     out = None
     for it in range(args.warmup):
@@ -149,6 +153,7 @@ def main():
                           "n_gpus": world, "ms_per_step": t.item(), "per_gpu_batch": args.batch, "image": args.image, "z_dim": args.zdim,
                           "last_losses": {k: (round(v, 5) if v is not None else None) for k, v in out.items()},
                           "params_M": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
+                          "exchange": ("peer memory" if (group is not None and args.peer) else ("nccl" if group is not None else "none")),
                           "note": "fp32 (TF32 convs off), stock torch conv modules, all loss terms through libtcelbo.so, eager launches"}), flush=True)
     if world > 1:
         dist.barrier()
