@@ -108,6 +108,30 @@ def backward_rowvar(fw, g_log_qz, g_log_qz_prod):
     return grad_z, grad_mu, grad_lv
 
 
+def backward_rowvar_sweep(fw, g_log_qz, g_log_qz_prod):
+    """The same gradients with the fused sweep's own arithmetic (csrc/tc_bwd_fused.cu: bwd_pairs): the exponent is carried
+    shifted, q' = dl^2 - 1/(2 ln2), so that 2 ln2 qc - 1 = 2 ln2 qc' and the logvar sum is sum_j r qc'; e is recomputed as
+    2^-qc' = e * exp(1/2) with the exp(-1/2) folded into gP/S."""
+    p = fw["pro"]
+    k = F(1) / (F(2) * LN2)
+    rsqrt_e = F(np.exp(-0.5))
+    gJ = g_log_qz.astype(F)[:, None]
+    gps = (g_log_qz_prod.astype(F)[:, None] / fw["S"]) * rsqrt_e                    # [R,D]
+    qw = gJ * np.exp2(fw["x"] - fw["J2"][:, None])                                 # gJ_i * q_ij
+    qs = fw["dl"] * fw["dl"] - k
+    qmax_s = p["qmax"][:, None, :] - k
+    cs = np.minimum(qs, qmax_s)
+    es = np.exp2(-cs) * fw["rho"][:, :, None]
+    coef = es * gps[:, None, :] + qw[:, :, None]
+    r = coef * (qs <= qmax_s).astype(F)
+    t = r * fw["dl"]
+    two_ln2 = F(2) * LN2
+    grad_z = two_ln2 * p["ns"] * t.sum(axis=1, dtype=F)
+    grad_lv = p["vr"] * (two_ln2 * (r * cs).sum(axis=1, dtype=F))
+    grad_mu = -two_ln2 * (t * p["ns"][:, None, :]).sum(axis=0, dtype=F)
+    return grad_z, grad_mu, grad_lv
+
+
 def col_prologue(mu_all, lv_all):
     """Per-(j,d) constants of the column-variance ('full') density, ops.py:24-29."""
     mu_all, lv_all = mu_all.astype(F), lv_all.astype(F)

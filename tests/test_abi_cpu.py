@@ -96,6 +96,10 @@ def test_kernel_formulation_model_matches_reference(golden):
         assert rel(gz, golden[pre + "simple_mean_dz_partial"]) < 1e-4
         assert rel(gmu + gz + mu / B, golden[pre + "simple_mean_dmu"]) < 1e-4
         assert rel(glv + gz * eps * std * 0.5 - 0.5 * (1 - np.exp(lv)) / B, golden[pre + "simple_mean_dlv"]) < 1e-4
+        gz2, gmu2, glv2 = K.backward_rowvar_sweep(fw, g, -g)            # the sweep's shifted-exponent arithmetic
+        assert rel(gz2, golden[pre + "simple_mean_dz_partial"]) < 1e-4
+        assert rel(gmu2 + gz2 + mu / B, golden[pre + "simple_mean_dmu"]) < 1e-4
+        assert rel(glv2 + gz2 * eps * std * 0.5 - 0.5 * (1 - np.exp(lv)) / B, golden[pre + "simple_mean_dlv"]) < 1e-4
         fj = K.forward_colvar(z, mu, lv, N, "mss")
         assert rel(fj["log_qz_prod"], golden[pre + "varj_log_qz_prod"]) < 1e-5
         assert rel(fj["log_qz"], golden[pre + "varj_log_qz"]) < 1e-5
