@@ -37,13 +37,15 @@ int fail_cuda(cudaError_t e, const char* what) {
 }
 
 int sm_count() {
-    static int cached = 0;
-    if (cached > 0) return cached;
+    static PerDevice cached_on;
     int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
-        cached = sms;
-        return sms;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        int& cached = cached_on.cur();
+        if (cached > 0) return cached;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
+            cached = sms;
+            return sms;
+        }
     }
     (void)cudaGetLastError();
     return 148;                                   // B200; only reached when no device is visible (size queries on a CPU box)

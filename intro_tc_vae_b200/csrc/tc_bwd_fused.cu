@@ -508,7 +508,8 @@ static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, BwdFinArgs*
     constexpr int ROWS = NW * RI;
     const size_t smem = ((size_t)kStages * GEO::JT * GEO::DP + (size_t)kStages * ROWS * GEO::JT + (size_t)NW * RI * GEO::JT
                          + NBUF * (size_t)NW * GEO::JS * GEO::DP) * sizeof(float) + (2 * kStages + 2 * NBUF) * sizeof(uint64_t);
-    static int ctas_per_sm = 0;
+    static PerDevice ctas_on;
+    int& ctas_per_sm = ctas_on.cur();
     if (ctas_per_sm == 0) {
         auto kern = tc_bwd_fused_kernel<DPT, RI, NW, MINB, JS_, PHASED, NBUF, ABL, SCALAR, JTMAX>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

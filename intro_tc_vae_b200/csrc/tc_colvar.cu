@@ -413,7 +413,8 @@ template <int LPR>
 static cudaError_t launch_fwd_colvar_t(const Plan& p, FwdArgs a, int* n_js_out, cudaStream_t st) {
     using GEO = CvGeom<LPR>;
     const size_t smem = (size_t)kStages * GEO::TILE * sizeof(float) + 2 * kStages * sizeof(uint64_t);
-    static int ctas_per_sm = 0;
+    static PerDevice ctas_on;
+    int& ctas_per_sm = ctas_on.cur();
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(tc_fwd_colvar_kernel<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -449,7 +450,8 @@ static cudaError_t launch_bwd_colvar_t(const Plan& p, BwdFusedArgs a, int* n_js_
     constexpr int ROWS = kBwdWarps * RI;
     const size_t smem = ((size_t)kStages * GEO::JT * 3 * GEO::DP + (size_t)kStages * ROWS * GEO::JT + (size_t)kBwdWarps * RI * GEO::JT
                          + (size_t)kBwdWarps * GEO::JS * 2 * GEO::DP) * sizeof(float) + 2 * kStages * sizeof(uint64_t);
-    static int ctas_per_sm = 0;
+    static PerDevice ctas_on;
+    int& ctas_per_sm = ctas_on.cur();
     if (ctas_per_sm == 0) {
         auto kern = tc_bwd_colvar_kernel<DPT, RI>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

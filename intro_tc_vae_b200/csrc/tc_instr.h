@@ -25,4 +25,11 @@ struct LaunchScope {                        // RAII: count the launch, record ev
     ~LaunchScope() { if (timed) cudaEventRecord(instr().ev_stop, st); }
 };
 
+// One cached int per CUDA device (cudaFuncSetAttribute and occupancy are per device: a process that drives several GPUs
+// must configure every kernel on each of them).  Races are benign: every thread computes the same value.
+struct PerDevice {
+    int v[64] = {};
+    int& cur() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) d = 0; return v[d & 63]; }
+};
+
 }  // namespace tcelbo

@@ -376,11 +376,12 @@ static cudaError_t launch_fwd_t(const Plan& p, const FwdArgs& a, cudaStream_t st
     constexpr int DP = 32 * LPR;
     constexpr int JT = (kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP);
     const size_t smem = (size_t)kStages * JT * DP * sizeof(float) + 2 * kStages * sizeof(uint64_t);
-    static bool configured = false;
+    static PerDevice configured_on;
+    int& configured = configured_on.cur();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured = 1;
     }
     LaunchScope scope(kKernFwd, st);
     tc_fwd_kernel<LPR><<<p.seg_fwd.n_ctas, kFwdWarps * 32, smem, st>>>(a);

@@ -58,10 +58,18 @@ class GraphedKLLoss:
                     from . import peer
                     try:
                         self.exchange = peer.PeerExchange(b_loc, d, group, self.device)
-                        self.exchange_kind = "peer"
                     except Exception:
                         if exchange == "peer":
                             raise
+                    # the choice is collective: one rank without symmetric memory puts every rank on NCCL
+                    ok = torch.tensor([1 if self.exchange is not None else 0], device=self.device)
+                    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                    if int(ok.item()) == 0:
+                        if exchange == "peer":
+                            raise RuntimeError("tcelbo: the peer-memory exchange could not be set up on every rank of the group")
+                        self.exchange = None
+                    else:
+                        self.exchange_kind = "peer"
         self.b_loc, self.d = int(b_loc), int(d)
         self.mu = torch.zeros(b_loc, d, device=self.device, requires_grad=(mode == "autograd"))
         self.logvar = torch.zeros(b_loc, d, device=self.device, requires_grad=(mode == "autograd"))
