@@ -380,6 +380,7 @@ def run_ours(args):
             "ex2_measured_gps": ex2_measured / 1e9, "frac_of_measured_ex2": achieved / ex2_measured,
             "peak_at_observed_clock_gps": peak_at_clock / 1e9,
             "kernel_ms": kern_ms,
+            "kernel_frac_of_sfu_peak": {k: alg_fwd / (v * 1e-3) / peak_nominal for k, v in kern_ms.items()},
             "step_algorithmic_ex2": 2 * B * B * D + 2 * B * B,
             "step_frac_of_sfu_peak": (2 * B * B * D + 2 * B * B) / world / (ms_per_step * 1e-3) / peak_nominal,
             "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_bytes / (ms_per_step * 1e-3) / 1e9,
