@@ -149,6 +149,7 @@ __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, cons
     using GEO = BwdGeom<DPT, JS_, JTMAX>;
     constexpr int VEC = GEO::VEC, NCH = GEO::NCH, DP = GEO::DP, CH = GEO::CH, JT = GEO::JT, JS = GEO::JS, GV = GEO::GV, NP = GEO::NP;
     constexpr int RG = (RI % 2 == 0) ? 2 : 1;
+    u64 mu_next[BwdGeom<DPT, JS_, JTMAX>::NP];
 #pragma unroll 1
     for (int g0 = 0; g0 < JS; g0 += GV) {
         float gqv[RI][GV];
@@ -157,22 +158,31 @@ __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, cons
             if (ABL == 3) { for (int u = 0; u < GV; ++u) gqv[r][u] = 1e-3f * (float)(r + 1); }      // ABL 3: no joint-coefficient loads
             else VecLd<GV>::ld(gq + r * JT + sub + g0, gqv[r]);
         }
+        auto load_mu = [&](int col, u64 (&dst)[NP]) {
+            float vm[DPT];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                float v[VEC];
+                VecLd<VEC>::ld(tile + col * DP + c * CH + VEC * lane, v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) vm[c * VEC + e] = v[e];
+            }
+#pragma unroll
+            for (int p = 0; p < NP; ++p) dst[p] = pack2(vm[2 * p], DPT >= 2 ? vm[(2 * p + 1) % DPT] : 0.0f);
+        };
+        // column u+1's operand is loaded while column u computes: the LDS latency (29 cycles, 14 % of the stall samples when
+        // loaded just in time) hides behind a whole column of math.  Carrying the prefetch across the 4-column groups
+        // (ABL 4, experiment) measured 4 % slower than restarting it per group.
+        if (ABL != 4 || g0 == 0) load_mu(sub + g0, mu_next);
 #pragma unroll
         for (int u = 0; u < GV; ++u) {
             const int jj = sub + g0 + u;
             u64 mu2[NP], G2[NP];
-            {
-                float vm[DPT];
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    float v[VEC];
-                    VecLd<VEC>::ld(tile + jj * DP + c * CH + VEC * lane, v);
+            for (int p = 0; p < NP; ++p) mu2[p] = mu_next[p];
+            if (u + 1 < GV || (ABL == 4 && g0 + GV < JS)) load_mu(jj + 1, mu_next);
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) vm[c * VEC + e] = v[e];
-                }
-#pragma unroll
-                for (int p = 0; p < NP; ++p) { mu2[p] = pack2(vm[2 * p], DPT >= 2 ? vm[(2 * p + 1) % DPT] : 0.0f); G2[p] = 0ull; }
-            }
+            for (int p = 0; p < NP; ++p) G2[p] = 0ull;
             float rho[RI];
 #pragma unroll
             for (int r = 0; r < RI; ++r) {
@@ -546,6 +556,7 @@ cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* f
                 case 11: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 3>(p, a, fin, st);          // three staging buffers
                 case 12: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 3, 0, false, 8>(p, a, fin, st);   // three 8-column staging buffers, 8-column tiles
                 case 13: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, false, 8>(p, a, fin, st);   // 8-column tiles only (control for 12)
+                case 14: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 4>(p, a, fin, st);             // operand prefetch carried across the 4-column groups
                 case 30: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, true>(p, a, fin, st); // scalar predicated loop
                 case 20: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 1>(p, a, fin, st);       // ablation: no column-gradient path
                 case 21: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 2>(p, a, fin, st);       // ablation: no MUFU
