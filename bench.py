@@ -59,6 +59,11 @@ def cpu_step(mu, lv, eps, n, beta):
 
 
 def time_cpu(b, d, steps, warmup):
+    # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to its workers; the baseline must not inherit that)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     mu, lv, eps = synthetic_latents(b, d)
     for _ in range(warmup):
         cpu_step(mu, lv, eps, DATASET_SIZE, BETA)
