@@ -150,7 +150,7 @@ __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, cons
     constexpr int VEC = GEO::VEC, NCH = GEO::NCH, DP = GEO::DP, CH = GEO::CH, JT = GEO::JT, JS = GEO::JS, GV = GEO::GV, NP = GEO::NP;
     constexpr int RG = (RI % 2 == 0) ? 2 : 1;
     u64 mu_next[BwdGeom<DPT, JS_, JTMAX>::NP];
-#pragma unroll 1
+#pragma unroll(ABL == 5 ? 1 : 4)
     for (int g0 = 0; g0 < JS; g0 += GV) {
         float gqv[RI][GV];
 #pragma unroll
@@ -171,16 +171,17 @@ __device__ __forceinline__ void bwd_subtile(const float* __restrict__ tile, cons
             for (int p = 0; p < NP; ++p) dst[p] = pack2(vm[2 * p], DPT >= 2 ? vm[(2 * p + 1) % DPT] : 0.0f);
         };
         // column u+1's operand is loaded while column u computes: the LDS latency (29 cycles, 14 % of the stall samples when
-        // loaded just in time) hides behind a whole column of math.  Carrying the prefetch across the 4-column groups
-        // (ABL 4, experiment) measured 4 % slower than restarting it per group.
-        if (ABL != 4 || g0 == 0) load_mu(sub + g0, mu_next);
+        // loaded just in time) hides behind a whole column of math.  The group loop is fully unrolled so that all JS columns
+        // of the sub-tile form one basic block and the prefetch chain runs through it (ABL 5, control: one group per
+        // iteration, prefetch restarted per group: +3.5 % time).
+        if (ABL == 5 || g0 == 0) load_mu(sub + g0, mu_next);
 #pragma unroll
         for (int u = 0; u < GV; ++u) {
             const int jj = sub + g0 + u;
             u64 mu2[NP], G2[NP];
 #pragma unroll
             for (int p = 0; p < NP; ++p) mu2[p] = mu_next[p];
-            if (u + 1 < GV || (ABL == 4 && g0 + GV < JS)) load_mu(jj + 1, mu_next);
+            if (u + 1 < GV || (ABL != 5 && g0 + GV < JS)) load_mu(jj + 1, mu_next);
 #pragma unroll
             for (int p = 0; p < NP; ++p) G2[p] = 0ull;
             float rho[RI];
@@ -556,7 +557,7 @@ cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* f
                 case 11: return launch_bwd_fused_t<4, 3, 8, 2, 4, false, 3>(p, a, fin, st);          // three staging buffers
                 case 12: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 3, 0, false, 8>(p, a, fin, st);   // three 8-column staging buffers, 8-column tiles
                 case 13: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, false, 8>(p, a, fin, st);   // 8-column tiles only (control for 12)
-                case 14: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 4>(p, a, fin, st);             // operand prefetch carried across the 4-column groups
+                case 14: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 5>(p, a, fin, st);             // control: 4-column basic blocks, prefetch restarted per group
                 case 30: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, true>(p, a, fin, st); // scalar predicated loop
                 case 20: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 1>(p, a, fin, st);       // ablation: no column-gradient path
                 case 21: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 2>(p, a, fin, st);       // ablation: no MUFU
