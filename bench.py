@@ -9,8 +9,8 @@ Workload at every N: BASELINE configs[2] at the size the north-star target is qu
 latents, GLOBAL batch 8192, z_dim 128 (strong scaling: rank r owns rows [r*B/N, (r+1)*B/N), mu is
 all-gathered over NCCL before the sweep and its gradient reduce-scattered after it).
 
-Prints ONE JSON line on rank 0 (see the keys below).  `--impl reference` times the CPU oracle port of
-the reference's implementation on the host cores (the reference itself is Python/torch and cannot travel).
+Prints ONE JSON line on rank 0 (see the keys below).  `--impl reference` times the reference's own CPU implementation on the
+host cores: the unmodified ops.py staged under oracle/_ref by __graft_entry__.build() (the oracle port if that is absent).
 """
 from __future__ import annotations
 
@@ -46,16 +46,33 @@ def synthetic_latents(b, d, seed=1234):
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port on the host cores
+# reference arm / cpu_baseline: the reference's own CPU implementation on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_step(mu, lv, eps, n, beta):
-    from oracle import tc_oracle as O
+def cpu_impl():
+    """(module, kind): the UNMODIFIED reference's ops.py staged under oracle/_ref (kind "reference"; oracle/ref_loader.py
+    copies it there wherever /root/reference exists and the copy travels with the snapshot), else the oracle port."""
+    from oracle import ref_loader
+    if ref_loader.available():
+        return ref_loader.load_ops(), "reference"
+    from oracle import tc_oracle
+    return tc_oracle, "port"
+
+
+def cpu_step(impl, mu, lv, n, beta):
+    """One compute_kl_loss-equivalent step exactly as the reference composes it: reparameterize (ops.py:166-185, draws its own
+    eps), kl_divergence + total_correlation -> (beta-1)*tc + kl (solvers/tc.py:83-89), backward.  Returns (fwd_s, bwd_s)."""
     mu = mu.detach().requires_grad_(True)
     lv = lv.detach().requires_grad_(True)
-    z = O.reparameterize(mu, lv, eps)
-    loss = O.kl_loss_simple(z, mu, lv, n, beta, "mean")
+    t0 = time.perf_counter()
+    z = impl.reparameterize(mu, lv)
+    kl = impl.kl_divergence(lv, mu, reduce="mean")
+    tc = impl.total_correlation(z, mu, lv, n, reduce="mean")
+    loss = (beta - 1.0) * tc + kl
+    loss.item()
+    t1 = time.perf_counter()
     loss.backward()
-    return loss.item()
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
 
 
 def time_cpu(b, d, steps, warmup):
@@ -64,15 +81,20 @@ def time_cpu(b, d, steps, warmup):
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:
         torch.set_num_threads(max(1, os.cpu_count() or 1))
-    mu, lv, eps = synthetic_latents(b, d)
+    impl, kind = cpu_impl()
+    mu, lv, _ = synthetic_latents(b, d)
     for _ in range(warmup):
-        cpu_step(mu, lv, eps, DATASET_SIZE, BETA)
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        cpu_step(mu, lv, eps, DATASET_SIZE, BETA)
-        times.append(time.perf_counter() - t0)
-    return times
+        cpu_step(impl, mu, lv, DATASET_SIZE, BETA)
+    times = [cpu_step(impl, mu, lv, DATASET_SIZE, BETA) for _ in range(steps)]
+    return times, kind
+
+
+def cpu_sample_note(b, d, kind, cores):
+    what = ("the UNMODIFIED reference (ops.reparameterize / kl_divergence / total_correlation from the staged oracle/_ref/ops.py)"
+            if kind == "reference" else "the oracle port of the reference's op sequence (oracle/tc_oracle.py)")
+    return (f"B={b}, D={d}, N={DATASET_SIZE}: reparameterize + kl_divergence + total_correlation + backward, fp32, {what}, "
+            f"{cores} torch threads of {os.cpu_count()} cpus; the reference keeps 4*B^2*D*4 bytes for backward (128 GiB at B=8192), "
+            "so it is timed on this bounded sample and compared as a rate")
 
 
 def run_reference(args):
@@ -80,19 +102,27 @@ def run_reference(args):
     if rank != 0:
         return 0
     b, d = CPU_SAMPLE_B, args.zdim
-    times = time_cpu(b, d, args.steps, args.warmup)
-    t = sum(times) / len(times)
+    times, kind = time_cpu(b, d, args.steps, args.warmup)
+    t = sum(f + w for f, w in times) / len(times)
     value = b * b * d / t
     cores = torch.get_num_threads()
-    sample = (f"B={b}, D={d}, N={DATASET_SIZE}: reparameterize + kl_divergence + total_correlation + backward, fp32, "
-              f"oracle port of the reference's op sequence (oracle/tc_oracle.py), {cores} torch threads of {os.cpu_count()} cpus")
+    # second, larger sample (BASELINE.md section 4 plan): B=2048 keeps 8 GiB for backward; two timed steps bound its cost
+    extra = []
+    try:
+        t2, _ = time_cpu(2 * b, d, 2, 1)
+        extra.append({"batch": 2 * b, "fwd_ms": 1e3 * min(f for f, _ in t2), "bwd_ms": 1e3 * min(w for _, w in t2),
+                      "value": (2 * b) ** 2 * d / min(f + w for f, w in t2)})
+    except Exception as exc:                             # e.g. a host without 8 GiB to spare
+        extra.append({"batch": 2 * b, "error": f"{type(exc).__name__}: {exc}"[:120]})
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"tc_microbench: global batch 8192, z_dim {d} (timed on a bounded CPU sample: B={b})",
+        "config": {"workload": f"tc_microbench (BASELINE configs[2]): global batch 8192, z_dim {d} (timed on a bounded CPU sample: B={b})",
                    "sample_batch": b, "z_dim": d, "dataset_size": DATASET_SIZE, "beta": BETA},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_note(b, d, kind, cores),
+                         "fwd_ms": 1e3 * sum(f for f, _ in times) / len(times), "bwd_ms": 1e3 * sum(w for _, w in times) / len(times),
+                         "more_samples": extra},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -396,12 +426,12 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N == 1 only): bounded sample of the same workload on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times = time_cpu(CPU_SAMPLE_B, D, steps=3, warmup=1)
-        t = min(times)
+        times, kind = time_cpu(CPU_SAMPLE_B, D, steps=3, warmup=1)
+        t = min(f + w for f, w in times)
         cores = torch.get_num_threads()
-        cpu = {"value": CPU_SAMPLE_B * CPU_SAMPLE_B * D / t, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"B={CPU_SAMPLE_B}, D={D}, N={N}: same step (reparameterize + KL + TC + backward) through the oracle "
-                         f"port of the reference's op sequence, fp32, best of 3, {cores} torch threads of {os.cpu_count()} cpus"}
+        cpu = {"value": CPU_SAMPLE_B * CPU_SAMPLE_B * D / t, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": cpu_sample_note(CPU_SAMPLE_B, D, kind, cores) + ", best of 3",
+               "fwd_ms": 1e3 * min(f for f, _ in times), "bwd_ms": 1e3 * min(w for _, w in times)}
 
     if rank == 0:
         line = {

@@ -559,9 +559,11 @@ cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* f
                 case 13: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, false, 8>(p, a, fin, st);   // 8-column tiles only (control for 12)
                 case 14: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 5>(p, a, fin, st);             // control: 4-column basic blocks, prefetch restarted per group
                 case 30: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 0, true>(p, a, fin, st); // scalar predicated loop
+#ifdef TCELBO_ABLATIONS                              // timing ablations return WRONG gradients: never in the shipped library
                 case 20: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 1>(p, a, fin, st);       // ablation: no column-gradient path
                 case 21: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 2>(p, a, fin, st);       // ablation: no MUFU
                 case 22: return launch_bwd_fused_t<4, 3, 8, 2, 8, false, 2, 3>(p, a, fin, st);       // ablation: no joint-coefficient loads
+#endif
                 default: return launch_bwd_fused_t<4, 3, 8, 2, 8, false>(p, a, fin, st);             // best of the sweep
             }
         case 8: case 16:                             // D = 256 / 512: the tuned 128-dim kernel over 2 / 4 slices (grid.z)

@@ -36,9 +36,14 @@ __global__ void colvar_prep_kernel(const float* __restrict__ z, int64_t ldz, con
             float sj = 0.f, nmus = 0.f, c2 = 0.f;
             if (j < b_glob && dd < d) {
                 const float lv = lv_all[(int64_t)j * ldlv + dd], m = mu_all[(int64_t)j * ldmu + dd];
-                sj = sqrtf(0.5f * kLog2e * expf(-lv));
-                nmus = -(m * sj);
+                const float iv = expf(-lv);
+                sj = sqrtf(0.5f * kLog2e * iv);
                 c2 = -0.5f * (lv + kLog2Pi) * kLog2e;
+                // logvar < -88.7: exp(-logvar) is +inf in fp32, so ops.py:27-29 yields -inf -> -50 for every z != mu.  Keep that
+                // behaviour with finite operands (dl^2 overflows to +inf and the clamp takes over) instead of inf - inf = NaN,
+                // and keep the unshifted sum S = sum_j rho 2^t finite: c2 stays <= 63 for every column that can be unclamped.
+                if (isinf(iv)) { sj = 1.0e19f; c2 = 0.0f; }
+                nmus = -(m * sj);
             }
             float* o = colpack + (size_t)j * 3 * dp + dd;
             o[0] = sj; o[dp] = nmus; o[2 * dp] = c2;

@@ -21,10 +21,11 @@ import torch
 from torch import Tensor
 
 from . import _lib
+from .losses import reconstruction_loss          # ops.py:188-236 lives in ops in the reference
 from .sharding import gather_rows, shard_rows
 
 __all__ = [
-    "total_correlation", "tc_terms", "kl_tc_loss_terms", "kl_divergence", "kl_no_reduce", "reparameterize",
+    "total_correlation", "tc_terms", "kl_tc_loss_terms", "kl_tc_loss_mean", "reconstruction_loss", "kl_divergence", "kl_no_reduce", "reparameterize",
     "log_importance_weight_matrix", "row_log_density", "gaussian_log_density_torch", "gaussian_log_density",
     "minibatch_stratified_sampling", "minibatch_weighted_sampling",
 ]
@@ -53,6 +54,20 @@ def _rows(t: Tensor) -> Tensor:
 
 def _stream(t: Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _alert_not_deterministic(what: str) -> None:
+    """The backward sweeps add per-CTA partial column sums into grad_mu (and grad_logvar of the column-variance variant)
+    with fp32 ``red.global.add``: the summation order, hence the last bits (~1e-7 relative), vary from launch to launch,
+    whereas the reference's autograd path is deterministic.  Same contract as torch's own non-deterministic ops."""
+    if torch.are_deterministic_algorithms_enabled():
+        msg = (f"{what} does not have a deterministic implementation (fp32 atomic accumulation of the column gradient), but "
+               "torch.use_deterministic_algorithms(True) is set")
+        if torch.is_deterministic_algorithms_warn_only_enabled():
+            import warnings
+            warnings.warn(msg)
+        else:
+            raise RuntimeError(msg + "; pass warn_only=True to run it anyway")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -88,6 +103,7 @@ def _(z, mu_all, logvar, row_offset, dataset_size, flags):
 @torch.library.custom_op("tcelbo::tc_backward", mutates_args=(), device_types="cuda")
 def _tc_backward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, dataset_size: int, flags: int,
                  g_log_qz: Tensor, g_log_qz_prod: Tensor, workspace: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    _alert_not_deterministic("tcelbo::tc_backward")
     lib = _lib.load()
     z, mu_all, logvar = _rows(z), _rows(mu_all), _rows(logvar)
     b_loc, d = z.shape
@@ -175,6 +191,7 @@ def _(z, mu_all, logvar, row_offset, dataset_size, flags, beta):
 def _klloss_backward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, dataset_size: int, flags: int, beta: float,
                      g_loss: Tensor, g_kl: Optional[Tensor], g_log_qz: Optional[Tensor], g_log_qz_prod: Optional[Tensor],
                      workspace: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    _alert_not_deterministic("tcelbo::klloss_backward")
     lib = _lib.load()
     z, mu_all, logvar = _rows(z), _rows(mu_all), _rows(logvar)
     b_loc, d = z.shape
@@ -255,12 +272,20 @@ def kl_tc_loss_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, b
     if group is not None:
         import torch.distributed as dist
         if dist.get_world_size(group) > 1:
-            row_offset, _ = shard_rows(group, z.shape[0])
+            row_offset, _ = shard_rows(group, z.shape[0], z.device)
             mu_all = gather_rows(mu, group)
     if estimator == "mss" and mu_all.shape[0] == 1:
         raise ZeroDivisionError("float division by zero")       # ops.py:44 with M = B-1 = 0
     loss, kl, log_qz, log_qz_prod, _ = _klloss_forward(z, mu_all, logvar, row_offset, int(dataset_size), flags, float(beta))
     return loss, kl, log_qz, log_qz_prod
+
+
+def kl_tc_loss_mean(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, beta: float, estimator: str = "mss",
+                    group=None, exchange=None) -> Tuple[Tensor, Tensor]:
+    """``reduce="mean"`` form of :func:`kl_tc_loss_terms`: 0-d ``(mean_i[(beta-1)*tc_i + kl_i], mean_i kl_i)``
+    (solvers/tc.py:83-89 with the default reduce).  Row-sharded calls return the mean over the local rows."""
+    loss, kl, _, _ = kl_tc_loss_terms(z, mu, logvar, dataset_size, beta, estimator, group, exchange)
+    return loss.mean(), kl.mean()
 
 
 def tc_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, estimator: str = "mss",
@@ -292,7 +317,7 @@ def tc_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, estimator
     if group is not None:
         import torch.distributed as dist
         if dist.get_world_size(group) > 1:
-            row_offset, _ = shard_rows(group, z.shape[0])
+            row_offset, _ = shard_rows(group, z.shape[0], z.device)
             mu_all = gather_rows(mu, group)
             if var_of == "col":
                 lv_op = gather_rows(logvar, group)

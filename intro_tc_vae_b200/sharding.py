@@ -38,8 +38,18 @@ def gather_rows(x: Tensor, group) -> Tensor:
     return GatherRows.apply(x, group)
 
 
-def shard_rows(group, b_loc: int) -> Tuple[int, int]:
-    """(row_offset, b_glob) of this rank for equal shards of ``b_loc`` rows."""
+def shard_rows(group, b_loc: int, device=None) -> Tuple[int, int]:
+    """(row_offset, b_glob) of this rank for equal shards of ``b_loc`` rows.
+
+    The row offsets and the importance weights assume every rank holds the same number of rows.  With ``device`` given the
+    shard sizes are all-gathered (one 8-byte collective, no host synchronisation) and a device-side assertion fails the
+    run loudly when they differ (e.g. a ragged last batch that is not ragged the same way on every rank) instead of
+    computing with wrong offsets or hanging in the all-gather of the rows."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    if device is not None and world > 1:
+        mine = torch.tensor([b_loc], dtype=torch.int64, device=device)
+        sizes = torch.empty(world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(sizes, mine, group=group)
+        torch._assert_async((sizes == b_loc).all(), "tcelbo: the ranks of the process group hold different numbers of rows")
     return dist.get_rank(group) * b_loc, world * b_loc

@@ -1,9 +1,10 @@
-"""TC loss composition with the reference's solver signatures (reference ``solvers/tc.py:22-144``).
+"""TC loss composition behind the reference's solver signatures (reference ``solvers/tc.py:58-144``).
 
-``TCLossMixin`` carries the three methods; ``TCSovler`` (the reference's spelling) binds it to the
-VAE train step.  Only ``self.beta_kl``, ``len(self.dataset)`` and ``self.write_scalar`` are read,
-so the mixin also serves ``IntroTCSovler`` (solvers/intro_tc.py:8-17) and, through
-``intro_tc_vae_b200.install()``, the reference's own solver classes.
+``TCLossMixin`` carries the three loss methods of ``TCSovler``; :func:`intro_tc_vae_b200.install` grafts them onto the
+reference's own ``solvers.tc.TCSovler`` (whose ``compute_kl_loss`` dispatches to ``self._compute_kl_loss_simple`` and which
+``solvers.intro_tc.IntroTCSovler`` forwards to, solvers/intro_tc.py:8-17), so the reference's ``train_step`` code runs
+unchanged on top of the fused kernels.  The methods only read ``self.beta_kl``, ``len(self.dataset)`` and
+``self.write_scalar``; this package ships no copy of the reference's solver classes.
 """
 from __future__ import annotations
 
@@ -12,8 +13,13 @@ from typing import Optional
 from torch import Tensor
 
 from .. import ops
-from ..utils import SingletonWriter
-from .vae import VAESolver
+from .. import utils as _utils
+
+
+def _singleton_writer():
+    """The process-wide writer holder the training driver updates: the reference's ``utils.SingletonWriter`` after
+    :func:`intro_tc_vae_b200.install` (train.py:100-103,212 set ``writer`` / ``cur_iter`` on it), this package's otherwise."""
+    return _utils.SingletonWriter()
 
 
 class TCLossMixin:
@@ -32,16 +38,22 @@ class TCLossMixin:
         if beta is None:
             beta = self.beta_kl
         dataset_size = len(self.dataset)
-        # one fused op: per-sample (beta-1)*tc_i + kl_i and kl_i (KL and the combine ride in the TC kernels' epilogues)
+        group = getattr(self, "process_group", None)
         exch = getattr(self, "peer_exchange", None)
         if exch is not None and tuple(z.shape) != (exch.b_loc, exch.d):
+            if group is None:
+                raise RuntimeError(
+                    f"tcelbo: batch shape {tuple(z.shape)} does not match the peer exchange ({exch.b_loc}, {exch.d}) and no "
+                    "process_group is set to fall back on: the estimator would silently run unsharded on the local rows")
             exch = None                                              # e.g. a ragged last batch: NCCL path
-        loss, kl, _, _ = ops.kl_tc_loss_terms(z, mu, logvar, dataset_size, beta, "mss", getattr(self, "process_group", None), exch)
-        if write:                                                    # KL only, as in the reference (solvers/tc.py:87-88)
-            kl_loss = kl.sum() if reduce == "sum" else (kl.mean() if reduce == "mean" else kl)
-            self.write_scalar(SingletonWriter().cur_iter, "kl_loss_unscaled", kl_loss)
         if reduce == "mean":                                         # mean((b-1)*tc + kl) == (b-1)*mean(tc) + mean(kl)
-            return loss.mean()
+            loss, kl = ops.kl_tc_loss_mean(z, mu, logvar, dataset_size, beta, "mss", group, exch)
+        else:
+            # one fused op: per-sample (beta-1)*tc_i + kl_i and kl_i (KL and the combine ride in the TC kernels' epilogues)
+            loss, kl, _, _ = ops.kl_tc_loss_terms(z, mu, logvar, dataset_size, beta, "mss", group, exch)
+        if write:                                                    # KL only, as in the reference (solvers/tc.py:87-88)
+            kl_loss = kl if reduce == "mean" else (kl.sum() if reduce == "sum" else kl)
+            self.write_scalar(_singleton_writer().cur_iter, "kl_loss_unscaled", kl_loss)
         if reduce == "sum":                                          # kl summed, tc per sample (ops.py:86-89 treats "sum" as none)
             return (loss - kl) + kl.sum()
         return loss
@@ -59,17 +71,14 @@ class TCLossMixin:
         mi_loss = logqz_condx - log_qz
         tc_loss = log_qz - logqz_prodmarginals
         kl_loss = logqz_prodmarginals - logpz
+        sw = _singleton_writer()
         if reduce == "mean":
             mi_loss, tc_loss, kl_loss = mi_loss.mean(), tc_loss.mean(), kl_loss.mean()
-            if SingletonWriter().writer:
-                SingletonWriter().writer.add_scalars(
+            if sw.writer:
+                sw.writer.add_scalars(
                     "tc_decomp",
                     {"mi": mi_loss.data.item(), "tc": tc_loss.data.item(), "kl": kl_loss.data.item()},
-                    global_step=SingletonWriter().cur_iter)
+                    global_step=sw.cur_iter)
         if write:
-            self.write_scalar(SingletonWriter().cur_iter, "kl_loss_unscaled", mi_loss + tc_loss + kl_loss)
+            self.write_scalar(sw.cur_iter, "kl_loss_unscaled", mi_loss + tc_loss + kl_loss)
         return mi_loss + beta * tc_loss + kl_loss
-
-
-class TCSovler(TCLossMixin, VAESolver):
-    """Same constructor as VAESolver (solvers/tc.py:23-55)."""

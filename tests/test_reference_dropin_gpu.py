@@ -1,0 +1,109 @@
+"""Drop-in check against the REAL reference (staged unmodified under oracle/_ref by oracle/ref_loader.py):
+
+* the reference's own ``IntroTCSovler.train_step`` / ``TCSovler.train_step`` (solvers/intro.py:56-196, solvers/vae.py:89-136)
+  on the reference's own ``SoftIntroVAE`` run on top of the kernels after ``intro_tc_vae_b200.install()``;
+* with identical seeds the installed step returns the same losses as the untouched reference run in eager torch on the
+  same GPU;
+* ``solver.compute_kl_loss`` of the installed reference equals the untouched reference's on the same encoder outputs.
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import ref_loader
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref not staged")]
+
+N_DATA = 16704
+
+
+class _Dataset:
+    def __len__(self):
+        return N_DATA
+
+
+def _build(solver_name, dev, installed, seed=0, B=48, zdim=32, image=16):
+    """Model + solver from the reference's modules (fresh import inside the current ref_loader.on_path() context)."""
+    import models
+    if installed:
+        import intro_tc_vae_b200
+        intro_tc_vae_b200.install()
+    from solvers.intro_tc import IntroTCSovler
+    from solvers.tc import TCSovler
+    from utils import SingletonWriter
+    SingletonWriter().writer = None                  # what train.py:100-103 does without TensorBoard
+    SingletonWriter().cur_iter = 0
+    torch.manual_seed(seed)
+    model = models.SoftIntroVAE(arch="conv", cdim=3, zdim=zdim, channels=(16, 32), image_size=image).to(dev)
+    opt_e = torch.optim.Adam(model.encoder.parameters(), lr=2e-4)
+    opt_d = torch.optim.Adam(model.decoder.parameters(), lr=2e-4)
+    common = dict(dataset=_Dataset(), model=model, batch_size=B, optimizer_e=opt_e, optimizer_d=opt_d, recon_loss_type="mse",
+                  beta_kl=0.5, beta_rec=0.75, device=dev, use_amp=False, grad_scaler=None, writer=None, test_iter=1000, clip=100.0)
+    if solver_name == "tc":
+        return model, TCSovler(**common)
+    return model, IntroTCSovler(**common, beta_neg=512.0, gamma_r=1e-8)
+
+
+@pytest.mark.parametrize("solver_name", ["tc", "intro-tc"])
+def test_reference_train_step_runs_on_the_kernels_and_matches_the_untouched_reference(solver_name):
+    dev = torch.device("cuda:0")
+    B = 48
+    batch = torch.rand(B, 3, 16, 16, generator=torch.Generator().manual_seed(5))
+    outs = {}
+    for installed in (False, True):
+        with ref_loader.on_path():
+            from intro_tc_vae_b200 import _lib
+            lib = _lib.load()
+            model, solver = _build(solver_name, dev, installed)
+            torch.manual_seed(11)                        # CPU generator: the fake-batch noise; CUDA generator: the reparameterize eps
+            torch.cuda.manual_seed(11)
+            c0 = lib.tcelbo_launch_count()
+            out = solver.train_step(batch, 0)
+            launched = lib.tcelbo_launch_count() - c0
+            assert all(math.isfinite(v) for v in out.values() if v is not None), out
+            # the installed reference must actually run the library's kernels; the untouched one must not
+            assert (launched > 0) == installed, (installed, launched)
+            with torch.no_grad():
+                mu, lv = model.encode(batch.to(dev))
+                eps = torch.randn(B, model.zdim, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+                z = mu + eps * torch.exp(0.5 * lv)
+                kl_mean = solver.compute_kl_loss(z, mu, lv)
+                kl_rows = solver.compute_kl_loss(z, mu, lv, reduce="none", beta=512.0)
+            outs[installed] = (out, kl_mean.item(), kl_rows.cpu())
+    ref, got = outs[False], outs[True]
+    for key in ("loss_enc", "loss_dec", "loss_kl", "loss_rec"):
+        assert abs(got[0][key] - ref[0][key]) <= 2e-4 * max(abs(ref[0][key]), 1e-3), (key, got[0][key], ref[0][key])
+    # after one optimizer step the two models' parameters differ in the last bits, so the post-step KL loss gets 1e-3
+    assert abs(got[1] - ref[1]) <= 1e-3 * abs(ref[1])
+    assert ((got[2] - ref[2]).abs().max() / ref[2].abs().max()).item() <= 1e-3
+
+
+def test_installed_compute_kl_loss_equals_reference_on_identical_latents():
+    """Identical (z, mu, logvar): the installed reference solver's compute_kl_loss (mean / none / explicit beta) vs the untouched
+    reference's own ops on the CPU, at the north-star tolerances, gradients included."""
+    dev = torch.device("cuda:0")
+    B, D = 96, 32
+    g = torch.Generator().manual_seed(17)
+    mu_c, lv_c, eps_c = torch.randn(B, D, generator=g), -2.0 + torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)
+    ref = {}
+    with ref_loader.on_path():
+        _, solver = _build("intro-tc", torch.device("cpu"), installed=False, B=B, zdim=D)
+        mu, lv = mu_c.clone().requires_grad_(True), lv_c.clone().requires_grad_(True)
+        z = mu + eps_c * torch.exp(0.5 * lv)
+        loss = solver.compute_kl_loss(z, mu, lv)
+        rows = solver.compute_kl_loss(z, mu, lv, reduce="none", beta=512.0)
+        (loss + 1e-3 * rows.mean()).backward()
+        ref = dict(loss=loss.item(), rows=rows.detach(), gmu=mu.grad, glv=lv.grad)
+    with ref_loader.on_path():
+        _, solver = _build("intro-tc", dev, installed=True, B=B, zdim=D)
+        mu, lv = mu_c.to(dev).requires_grad_(True), lv_c.to(dev).requires_grad_(True)
+        z = mu + eps_c.to(dev) * torch.exp(0.5 * lv)
+        loss = solver.compute_kl_loss(z, mu, lv)
+        rows = solver.compute_kl_loss(z, mu, lv, reduce="none", beta=512.0)
+        (loss + 1e-3 * rows.mean()).backward()
+        rel = lambda a, b: ((a.detach().cpu().double() - b.double()).abs().max() / b.double().abs().max()).item()   # noqa: E731
+        assert abs(loss.item() - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+        assert rel(rows, ref["rows"]) <= 1e-5
+        assert rel(mu.grad, ref["gmu"]) <= 1e-4
+        assert rel(lv.grad, ref["glv"]) <= 1e-4

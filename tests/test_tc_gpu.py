@@ -61,7 +61,7 @@ def test_golden_loss_terms_and_grads(golden, name, chunk_view):
     assert relerr(prod, golden[pre + "log_qz_prod"]) < LOSS_RTOL
     assert relerr(joint, golden[pre + "log_qz"]) < LOSS_RTOL
     tc = ops.total_correlation(z, mu, lv, N, reduce="none")
-    assert relerr(tc, golden[pre + "tc"]) < LOSS_RTOL * max(1.0, np.abs(golden[pre + "log_qz_prod"]).max() / np.abs(golden[pre + "tc"]).max())
+    assert relerr(tc, golden[pre + "tc"]) < LOSS_RTOL
     kl = ops.kl_divergence(lv, mu, reduce="none")
     assert relerr(kl, golden[pre + "kl"]) < LOSS_RTOL
     prod_w, joint_w = ops.tc_terms(z, mu, lv, N, "mws", "row")
@@ -70,8 +70,7 @@ def test_golden_loss_terms_and_grads(golden, name, chunk_view):
 
     # (beta-1)*tc + kl, mean-reduced, and its gradients through z = mu + eps*std  (solvers/tc.py:69-89)
     simple = (beta - 1.0) * ops.total_correlation(z, mu, lv, N, reduce="mean") + ops.kl_divergence(lv, mu, reduce="mean")
-    assert abs(simple.item() - float(golden[pre + "simple_mean"])) < LOSS_RTOL * abs(float(golden[pre + "simple_mean"])) * \
-        max(1.0, beta * np.abs(golden[pre + "log_qz_prod"]).mean() / abs(float(golden[pre + "simple_mean"])))
+    assert abs(simple.item() - float(golden[pre + "simple_mean"])) < LOSS_RTOL * abs(float(golden[pre + "simple_mean"]))
     gz = torch.autograd.grad(simple, z, retain_graph=True)[0]
     assert relerr(gz, golden[pre + "simple_mean_dz_partial"]) < GRAD_RTOL
     simple.backward(retain_graph=True)
@@ -87,10 +86,10 @@ def test_golden_loss_terms_and_grads(golden, name, chunk_view):
     # per-sample loss with an explicit beta and the soft-intro exp-ELBO on top (solvers/intro.py:84-103)
     simple_none = (beta - 1.0) * ops.total_correlation(z, mu, lv, N, reduce="none") + ops.kl_divergence(lv, mu, reduce="none")
     ref_none = golden[pre + "simple_none"]
-    assert relerr(simple_none, ref_none) < LOSS_RTOL * max(1.0, beta * np.abs(golden[pre + "log_qz_prod"]).max() / np.abs(ref_none).max())
+    assert relerr(simple_none, ref_none) < LOSS_RTOL
     rec_i = torch.arange(B, dtype=torch.float32, device="cuda:0") * 0.3
     ee = (-2 * (1.0 / (3 * 64 * 64)) * (rec_i + simple_none)).exp().mean()
-    assert abs(ee.item() - float(golden[pre + "expelbo"])) < LOSS_RTOL * abs(float(golden[pre + "expelbo"])) * 10
+    assert abs(ee.item() - float(golden[pre + "expelbo"])) < LOSS_RTOL * abs(float(golden[pre + "expelbo"]))
     ee.backward()
     if chunk_view:
         gmu, glv = leaf.grad.chunk(2, dim=1)
@@ -160,7 +159,7 @@ def test_seeded_inputs_against_cpu_oracle(B, D, family):
     loss.backward()
     assert relerr(prod, prod_o) < LOSS_RTOL
     assert relerr(joint, joint_o) < LOSS_RTOL
-    assert abs(loss.item() - loss_o.item()) < LOSS_RTOL * beta * prod_o.abs().mean().item()
+    assert abs(loss.item() - loss_o.item()) < LOSS_RTOL * abs(loss_o.item())
     assert relerr(mu.grad, mu_o.grad) < GRAD_RTOL
     assert relerr(lv.grad, lv_o.grad) < GRAD_RTOL
 
@@ -335,8 +334,7 @@ def test_golden_column_variance_and_full_decomposition(golden, name):
     solver = _FakeSolver(N, beta)
     full = TCLossMixin._compute_kl_loss_full(solver, z, mu, lv, "mean", None, True)
     ref = float(golden[pre + "full_mean"])
-    scale = max(1.0, beta * np.abs(golden[pre + "varj_log_qz_prod"]).mean() / abs(ref))
-    assert abs(full.item() - ref) < LOSS_RTOL * abs(ref) * scale
+    assert abs(full.item() - ref) < LOSS_RTOL * abs(ref)
     assert solver.written and solver.written[0][0] == "kl_loss_unscaled"
     full.backward()
     assert relerr(mu.grad, golden[pre + "full_mean_dmu"]) < GRAD_RTOL
@@ -356,8 +354,7 @@ def test_solver_mixin_simple_path(golden, name):
     solver = _FakeSolver(N, beta)
     loss = TCLossMixin.compute_kl_loss(solver, z, mu, lv, write=True)
     ref = float(golden[pre + "simple_mean"])
-    scale = max(1.0, beta * np.abs(golden[pre + "log_qz_prod"]).mean() / abs(ref))
-    assert loss.dim() == 0 and abs(loss.item() - ref) < LOSS_RTOL * abs(ref) * scale
+    assert loss.dim() == 0 and abs(loss.item() - ref) < LOSS_RTOL * abs(ref)
     loss.backward(retain_graph=True)                            # fused KL + TC backward, through z = mu + eps*std
     assert relerr(mu.grad, golden[pre + "simple_mean_dmu"]) < GRAD_RTOL
     assert relerr(lv.grad, golden[pre + "simple_mean_dlv"]) < GRAD_RTOL
@@ -367,11 +364,11 @@ def test_solver_mixin_simple_path(golden, name):
     per = TCLossMixin.compute_kl_loss(solver, z, mu, lv, reduce="none", beta=float(beta))
     assert per.shape == (case["B"],)
     ref_none = golden[pre + "simple_none"]
-    assert relerr(per, ref_none) < LOSS_RTOL * max(1.0, beta * np.abs(golden[pre + "log_qz_prod"]).max() / np.abs(ref_none).max())
+    assert relerr(per, ref_none) < LOSS_RTOL
     zero_beta = TCLossMixin.compute_kl_loss(solver, z, mu, lv, beta=0.0)          # an explicit 0.0 is honoured
     tc = ops.total_correlation(z, mu, lv, N)
     kl = ops.kl_divergence(lv, mu, reduce="mean")
-    assert abs(zero_beta.item() - (-tc + kl).item()) < 1e-3 * max(1.0, abs(zero_beta.item()))
+    assert abs(zero_beta.item() - (-tc + kl).item()) < LOSS_RTOL * abs(zero_beta.item())
 
 
 @pytest.mark.parametrize("B,D", [(256, 128), (96, 32), (48, 256)])
@@ -391,7 +388,7 @@ def test_column_variance_seeded_against_cpu_oracle(B, D):
     pz = ops.row_log_density(z)
     loss = (condx - joint).mean() + beta * (joint - prod).mean() + (prod - pz).mean()
     loss.backward()
-    assert abs(loss.item() - loss_o.item()) < LOSS_RTOL * beta * prod.abs().mean().item()
+    assert abs(loss.item() - loss_o.item()) < LOSS_RTOL * abs(loss_o.item())
     assert relerr(mu.grad, mu_o.grad) < GRAD_RTOL
     assert relerr(lv.grad, lv_o.grad) < GRAD_RTOL
 
@@ -421,49 +418,6 @@ def test_fused_loss_equals_composition(B, D, family):
     assert relerr(outs[1][1], outs[0][1]) < 2e-6
     assert relerr(outs[1][2], outs[0][2]) < 1e-5
     assert relerr(outs[1][3], outs[0][3]) < 1e-5
-
-
-@pytest.mark.parametrize("solver_name", ["tc", "intro-tc"])
-def test_solver_train_step_end_to_end(solver_name):
-    """Drop-in check of the solver classes: TCSovler / IntroTCSovler.train_step (solvers/vae.py:89-136,
-    solvers/intro.py:56-196) on a tiny conv VAE with chunk-view mu/logvar; losses finite, parameters move,
-    and the step's KL/TC loss equals the CPU oracle on the same encoder outputs."""
-    from tiny_model import TinyVAE
-    from intro_tc_vae_b200 import ops
-    from intro_tc_vae_b200.solvers import TCSovler, IntroTCSovler
-    torch.manual_seed(0)
-    dev = torch.device("cuda:0")
-    B, zdim = 48, 32
-    model = TinyVAE(3, zdim, 16, reparameterize=ops.reparameterize).to(dev)
-    opt_e = torch.optim.Adam(model.encoder.parameters(), lr=2e-4)
-    opt_d = torch.optim.Adam(model.decoder.parameters(), lr=2e-4)
-    dataset = _FakeDataset(16704)
-    common = dict(dataset=dataset, model=model, batch_size=B, optimizer_e=opt_e, optimizer_d=opt_d, recon_loss_type="mse",
-                  beta_kl=0.5, beta_rec=0.75, device=dev, use_amp=False, grad_scaler=None, writer=None, test_iter=1000, clip=100.0)
-    if solver_name == "tc":
-        solver = TCSovler(**common)
-    else:
-        solver = IntroTCSovler(**common, beta_neg=512.0, gamma_r=1e-8)
-    batch = torch.rand(B, 3, 16, 16)
-    before = [p.detach().clone() for p in model.parameters()]
-    for it in range(2):
-        out = solver.train_step(batch, it)
-        assert all(math.isfinite(v) for v in out.values() if v is not None), out
-    assert any((p.detach() - b).abs().max().item() > 0 for p, b in zip(model.parameters(), before))
-
-    with torch.no_grad():
-        mu, lv = model.encode(batch.to(dev))
-        eps = torch.randn(B, zdim, device=dev)
-        z = ops.reparameterize(mu, lv, eps)
-        got = solver.compute_kl_loss(z, mu, lv)
-        per = solver.compute_kl_loss(z, mu, lv, reduce="none", beta=512.0)
-    mu_c, lv_c = mu.cpu().contiguous(), lv.cpu().contiguous()
-    z_c = O.reparameterize(mu_c, lv_c, eps.cpu())
-    want = O.kl_loss_simple(z_c, mu_c, lv_c, 16704, 0.5, "mean")
-    want_per = O.kl_loss_simple(z_c, mu_c, lv_c, 16704, 512.0, "none")
-    prod_o, _ = O.tc_terms(z_c, mu_c, lv_c, 16704)
-    assert abs(got.item() - want.item()) < LOSS_RTOL * prod_o.abs().mean().item()
-    assert relerr(per, want_per) < LOSS_RTOL * max(1.0, 512.0 * prod_o.abs().max().item() / want_per.abs().max().item())
 
 
 @pytest.mark.parametrize("name", ["base_B64_D128", "stress_B64_D128", "ragged_B37_D20", "pair_B2_D16"])
