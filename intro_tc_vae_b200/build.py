@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libtcelbo.so")
-SOURCES = ["tc_kernels.cu", "tc_bwd_fused.cu", "tc_colvar.cu", "tc_materialized.cu", "tc_rowops.cu", "tc_abi.cu"]
+SOURCES = ["tc_kernels.cu", "tc_bwd_fused.cu", "tc_bwd_ds.cu", "tc_colvar.cu", "tc_materialized.cu", "tc_rowops.cu", "tc_abi.cu"]
 HEADERS = ["tc_common.cuh", "tc_kernels.h", "tc_layout.h", "tc_rowops.h", "tc_instr.h", "tc_materialized.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -42,7 +42,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA sources into intro_tc_vae_b200/libtcelbo.so; returns its path."""
     if not force and not _stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-I", CSRC]
+    extra = os.environ.get("TCELBO_NVCC_FLAGS", "").split()          # e.g. -DTCELBO_ABLATIONS for tools/tune_bwd.py
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-I", CSRC]
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

