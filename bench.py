@@ -351,7 +351,7 @@ def run_ours(args):
     # every rank runs these steps (they contain the collectives); only rank 0 brackets its kernels with events
     cur = torch.cuda.current_stream(dev)
     kern_ms = {}
-    for kid, name in ((1, "tc_fwd_kernel"), (2, "tc_bwd_fused_kernel")):
+    for kid, name in ((1, "tc_fwd_kernel"), (2, "tc_bwd_ds_kernel")):
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         ev0.record(cur); ev1.record(cur)               # materialise the underlying cudaEvent_t handles

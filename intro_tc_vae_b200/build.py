@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libtcelbo.so")
-SOURCES = ["tc_kernels.cu", "tc_bwd_fused.cu", "tc_bwd_ds.cu", "tc_colvar.cu", "tc_materialized.cu", "tc_rowops.cu", "tc_abi.cu"]
+SOURCES = ["tc_kernels.cu", "tc_bwd_ds.cu", "tc_colvar.cu", "tc_materialized.cu", "tc_rowops.cu", "tc_abi.cu"]
 HEADERS = ["tc_common.cuh", "tc_kernels.h", "tc_layout.h", "tc_rowops.h", "tc_instr.h", "tc_materialized.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,19 +1,27 @@
-// Fused backward sweep, "dims across warps" mapping (sm_100a).  Same arithmetic as tc_bwd_fused.cu (one MUFU.EX2 per
-// log-density, exponent carried shifted by 1/(2 ln2)), different ownership:
+// Fused backward sweep of the TC-ELBO estimator (sm_100a): ONE recomputation of e_ijd = 2^-qc per log-density yields all
+// three gradients of ops.py:80-115's autograd graph:
+//     r_ijd  = (gJ_i q_ij + gP_i rho_ij e_ijd / S_id) * [q_ijd <= qmax_id]      (mask of the -50 clamp)
+//     A_id   = sum_j r dl             -> grad_z        (row-local, registers)
+//     CR_id  = sum_j r (2 ln2 qc - 1) -> grad_logvar   (row-local, registers)
+//     G_jd   = sum_i r dl ns_id       -> grad_mu       (column sum over rows)
+// The exponent is carried shifted, q' = dl^2 - 1/(2 ln2) (one FFMA2), so that 2 ln2 qc - 1 = 2 ln2 qc' and the logvar sum is a
+// plain sum_j r qc'; 2^-qc' = e * exp(1/2) and the exp(-1/2) is folded into the per-row coefficient gP/S.
 //
+// Mapping ("dims across warps"):
 //   * a lane owns ONE latent dim; the CH warps of a row group cover a 32*CH-dim slice (CH = 4 at D >= 128), and every warp
 //     of the group holds the same 2*RP rows.  The two halves of a packed f32x2 register are two ROWS of that dim, so the
-//     column operand mu_jd is the same scalar in both halves and the per-(i,j) joint coefficients come out of shared
-//     memory already paired.
-//   * the column gradient G_jd = sum_i r dl ns_id of a warp's rows therefore accumulates in ONE register per column and
-//     goes straight to the global accumulator with a coalesced 128-byte red.global.add.f32 -- no shared-memory staging,
-//     no cross-warp reduction, no mbarrier hand-off between the warps of a CTA (13-15 % of the warp time of the
-//     row-across-warps kernel, profiles/r1_bwd_variant_sweep.md).  Warps meet only at the TMA pipeline's barriers.
+//     column operand mu_jd is one scalar broadcast into both halves (FFMA2's .F32 operand form) and the per-(i,j) joint
+//     coefficients come out of shared memory already paired.
+//   * the column gradient of a warp's rows therefore accumulates in ONE register per column and goes straight to the
+//     global accumulator with a coalesced 128-byte red.global.add.f32 -- no shared-memory staging, no cross-warp
+//     reduction, no mbarrier hand-off between the warps of a CTA (the rows-across-warps kernel of round 1 spent 13-15 % of
+//     its warp time in that hand-off, profiles/r1_bwd_variant_sweep.md; it is gone, profiles/r2_bwd_ds_sweep.md).  Warps meet
+//     only at the TMA pipeline's barriers.
 //   * both tile operands arrive by tensor-map TMA (cp.async.bulk.tensor.2d -> UTMALDG): a [JT x 32*CH] box of the padded
 //     column operand and a [ROWS x JT] box of the saved joint exponents s2 (rows past the padded batch are zero-filled by
 //     the TMA unit instead of clamped in software).
-//
-// Follows ops.py:80-115's autograd graph; see tc_bwd_fused.cu's header for the formulas.
+//   * D = 256 / 512 walk 128-dim slices: row-local and column sums are independent per dim, only the joint coefficients
+//     are shared, so a slice is a self-contained sweep (blocks = (slice, row block), balanced segments as in the forward).
 #include <cuda.h>
 
 #include "tc_common.cuh"
@@ -46,7 +54,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 }
 
 // One column for this warp's RP row pairs (this lane's dim).  kSpecial: the tile holds a stratified or a padding column.
-template <int RP, bool kSpecial>
+template <int RP, bool kSpecial, bool MSEL>
 __device__ __forceinline__ float ds_column(float mu, const float* __restrict__ gq_col, int i_glob0, int j, const Weights& w,
                                            const u64 (&zs2)[RP], const u64 (&ns2)[RP], const float (&qmx)[2 * RP],
                                            const u64 (&gps2)[RP], u64 (&A2)[RP], u64 (&CR2)[RP]) {
@@ -69,8 +77,14 @@ __device__ __forceinline__ float ds_column(float mu, const float* __restrict__ g
             e2 = fmul2(e2, pack2(r0, r1));
         }
         const u64 coef2 = ffma2(e2, gps2[p], gq2);
-        const u64 m2 = pack2(fset_le_ds(q0, qmx[2 * p]), fset_le_ds(q1, qmx[2 * p + 1]));
-        const u64 r2 = fmul2(coef2, m2);
+        u64 r2;
+        if (MSEL) {                                  // clamp mask as FSETP + FSEL on the ALU pipe (a NaN q gives r = 0, like torch.clamp's backward)
+            float k0, k1;
+            unpack2(coef2, k0, k1);
+            r2 = pack2(q0 <= qmx[2 * p] ? k0 : 0.0f, q1 <= qmx[2 * p + 1] ? k1 : 0.0f);
+        } else {                                     // FSET.BF + one packed multiply on the FMA pipe
+            r2 = fmul2(coef2, pack2(fset_le_ds(q0, qmx[2 * p]), fset_le_ds(q1, qmx[2 * p + 1])));
+        }
         const u64 t2 = fmul2(r2, dl2);
         A2[p] = fadd2(A2[p], t2);
         CR2[p] = ffma2(r2, pack2(c0, c1), CR2[p]);
@@ -120,7 +134,8 @@ __device__ __forceinline__ void ds_column_x2(float mu_a, float mu_b, const float
     unpack2(Gb, lo, hi); g_b = lo + hi;
 }
 
-template <int RP, int CH, int NW, int MINB, int JT, int BODY>
+// UNR: columns per basic block; X2: two columns in lockstep; MSEL: clamp mask by select (ALU pipe) instead of a packed multiply
+template <int RP, int CH, int NW, int MINB, int JT, int UNR, bool X2, bool MSEL>
 __global__ void __launch_bounds__(NW * 32, MINB)
 tc_bwd_ds_kernel(const __grid_constant__ BwdDsArgs a) {
     constexpr int RW = 2 * RP;                                               // rows per warp
@@ -135,7 +150,7 @@ tc_bwd_ds_kernel(const __grid_constant__ BwdDsArgs a) {
     float* mu_tiles = reinterpret_cast<float*>(smem_raw);                    // [kStages][JT][DPS]
     float* s2_tiles = mu_tiles + (size_t)kStages * TILE;                     // [kStages][ROWS][JT]
     float* gq_buf = s2_tiles + (size_t)kStages * ROWS * JT;                  // [NW][JT][RW]   (private per warp)
-    float* rowc = gq_buf + (size_t)NW * JT * RW;                             // [NW][RW][2]    gJ_i, J2_i of the warp's rows
+    float* rowc = gq_buf + (size_t)NW * JT * RW;                             // [NW][RW][2]    gJ_i, -J2_i of the warp's rows
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(rowc + (size_t)NW * RW * 2);
     uint64_t* bar_empty = bar_full + kStages;
 
@@ -178,8 +193,10 @@ tc_bwd_ds_kernel(const __grid_constant__ BwdDsArgs a) {
             const int row = row0 + lane;
             const bool valid = row < a.b_loc;
             const int rc = min(row, a.bl_pad - 1);
+            // rows past the batch: coefficient 0 * 2^(-inf) = 0 (their J2 is not written, and the s2 of rows past the padded batch
+            // is TMA zero fill: 2^(-J2 - 0) alone would overflow to inf for wide latents and 0 * inf poison the column sums)
             my_rowc[2 * lane] = valid ? __ldg(a.gj + rc) : 0.0f;
-            my_rowc[2 * lane + 1] = __ldg(a.J2 + rc);
+            my_rowc[2 * lane + 1] = valid ? -__ldg(a.J2 + rc) : -1.0e30f;
         }
         __syncwarp();
     };
@@ -235,18 +252,30 @@ tc_bwd_ds_kernel(const __grid_constant__ BwdDsArgs a) {
         const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
 
         // joint-term coefficients gJ_i q_ij of this warp's rows, transposed to [column][row] so that a column's RW values are
-        // RP ready-made f32x2 pairs (one broadcast LDS.64 each in the sweep)
+        // RP ready-made f32x2 pairs (one broadcast LDS.64 each in the sweep).  Value idx = lane + 32 k covers row lane/JT + RPI k
+        // and column lane % JT: every address is a per-lane base plus a compile-time offset.
         __syncwarp();
+        {
+            constexpr int RPI = 32 / JT;                                     // rows per iteration
+            const int jj = lane % JT, rl = lane / JT;
+            const float* s2p = s2t + lane;
+            const float* rcp = my_rowc + 2 * rl;
+            float* gqp = gq + jj * RW + rl;
+            if (special) {
 #pragma unroll
-        for (int k = 0; k < (RW * JT + 31) / 32; ++k) {
-            const int idx = lane + 32 * k;
-            if (idx < RW * JT) {
-                const int r = idx / JT, jj = idx % JT;
-                float rho = 1.0f, l2 = 0.0f;
-                if (special) weight_of(a.w, a.row_offset + row0 + r, jt0 + jj, rho, l2);
-                const float2 c = *reinterpret_cast<const float2*>(my_rowc + 2 * r);
-                const float qv = ex2(l2 - s2t[idx] - c.y);
-                gq[jj * RW + r] = (jt0 + jj < a.w.b_glob) ? c.x * qv : 0.0f;
+                for (int k = 0; k < RW / RPI; ++k) {
+                    float rho, l2;
+                    weight_of(a.w, a.row_offset + row0 + rl + RPI * k, jt0 + jj, rho, l2);
+                    const float2 c = *reinterpret_cast<const float2*>(rcp + 2 * RPI * k);
+                    const float qv = ex2(l2 - s2p[32 * k] + c.y);
+                    gqp[RPI * k] = (jt0 + jj < a.w.b_glob) ? c.x * qv : 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < RW / RPI; ++k) {
+                    const float2 c = *reinterpret_cast<const float2*>(rcp + 2 * RPI * k);   // (gJ_i, -J2_i)
+                    gqp[RPI * k] = c.x * ex2(c.y - s2p[32 * k]);
+                }
             }
         }
         __syncwarp();
@@ -255,12 +284,12 @@ tc_bwd_ds_kernel(const __grid_constant__ BwdDsArgs a) {
         if (special) {
 #pragma unroll 2
             for (int jj = 0; jj < JT; ++jj) {
-                const float g = ds_column<RP, true>(tile[jj * DPS], gq + jj * RW, a.row_offset + row0, jt0 + jj, a.w, zs2, ns2, qmx, gps2, A2, CR2);
+                const float g = ds_column<RP, true, MSEL>(tile[jj * DPS], gq + jj * RW, a.row_offset + row0, jt0 + jj, a.w, zs2, ns2, qmx, gps2, A2, CR2);
                 red_add_f32(gptr, g);
                 gptr += pitch;
             }
-        } else if (BODY == 1) {
-#pragma unroll 2
+        } else if (X2) {
+#pragma unroll(UNR / 2)
             for (int jj = 0; jj < JT; jj += 2) {
                 float ga, gb;
                 ds_column_x2<RP>(tile[jj * DPS], tile[(jj + 1) * DPS], gq + jj * RW, gq + (jj + 1) * RW, zs2, ns2, qmx, gps2, A2, CR2, ga, gb);
@@ -269,9 +298,9 @@ tc_bwd_ds_kernel(const __grid_constant__ BwdDsArgs a) {
                 gptr += 2 * pitch;
             }
         } else {
-#pragma unroll 4
+#pragma unroll(UNR)
             for (int jj = 0; jj < JT; ++jj) {
-                const float g = ds_column<RP, false>(tile[jj * DPS], gq + jj * RW, 0, 0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
+                const float g = ds_column<RP, false, MSEL>(tile[jj * DPS], gq + jj * RW, 0, 0, a.w, zs2, ns2, qmx, gps2, A2, CR2);
                 red_add_f32(gptr, g);
                 gptr += pitch;
             }
@@ -313,14 +342,14 @@ static bool make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64
 }
 
 static int g_ds_seg_target = 0;
-void set_bwd_ds_seg_target(int v) { g_ds_seg_target = v; }
+void set_bwd_seg_target(int v) { g_ds_seg_target = v; }
 
-template <int RP, int CH, int NW, int MINB, int JT, int BODY = 0>
+template <int RP, int CH, int NW, int MINB, int JT, int UNR = 8, bool X2 = false, bool MSEL = false>
 static cudaError_t launch_bwd_ds_t(const Plan& p, const BwdFusedArgs& u, BwdFinArgs* fin, cudaStream_t st) {
     constexpr int ROWS = (NW / CH) * 2 * RP, DPS = 32 * CH;
     const size_t smem = ((size_t)kStages * JT * DPS + (size_t)kStages * ROWS * JT + (size_t)NW * JT * 2 * RP + (size_t)NW * 2 * RP * 2) * sizeof(float)
                         + 2 * kStages * sizeof(uint64_t);
-    auto kern = tc_bwd_ds_kernel<RP, CH, NW, MINB, JT, BODY>;
+    auto kern = tc_bwd_ds_kernel<RP, CH, NW, MINB, JT, UNR, X2, MSEL>;
     static PerDevice ctas_on;
     int& ctas_per_sm = ctas_on.cur();
     if (ctas_per_sm == 0) {
@@ -349,21 +378,101 @@ static cudaError_t launch_bwd_ds_t(const Plan& p, const BwdFusedArgs& u, BwdFinA
     return cudaGetLastError();
 }
 
-// variant: 0 = 12 rows/warp, 16 warps/SM (default); 1 = 8 rows/warp, 24 warps/SM; 2 = 16 rows/warp, 12 warps/SM
-cudaError_t launch_bwd_ds(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* fin, int variant, cudaStream_t st) {
-    if (p.dp >= 128) {
-        switch (variant) {
-            case 1:  return launch_bwd_ds_t<4, 4, 8, 3, 16>(p, a, fin, st);
-            case 2:  return launch_bwd_ds_t<8, 4, 12, 1, 16>(p, a, fin, st);
-            case 3:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 1>(p, a, fin, st);       // two columns in lockstep
-            case 4:  return launch_bwd_ds_t<5, 4, 8, 2, 16, 1>(p, a, fin, st);       // 10 rows/warp, two columns in lockstep
-            case 5:  return launch_bwd_ds_t<5, 4, 8, 2, 16, 0>(p, a, fin, st);       // 10 rows/warp
-            case 6:  return launch_bwd_ds_t<4, 4, 12, 2, 16, 1>(p, a, fin, st);      // 8 rows/warp, 24 warps/SM (80 regs)
-            default: return launch_bwd_ds_t<6, 4, 8, 2, 16>(p, a, fin, st);
+// Elementwise over [B,D]: sum the column-split partials of the row-local sums (8 independent loads in flight), scale,
+// and add the fused KL gradient when asked (ops.py:161-163).
+__global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
+    const int64_t n_row = (int64_t)a.b_loc * a.d;
+    const int64_t n_col = a.scratch_parts != nullptr ? 0 : (int64_t)a.b_glob * a.d;
+    const size_t split_stride = (size_t)a.bl_pad * a.dp;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_row + n_col; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (idx < n_row) {
+            const int i = (int)(idx / a.d), dd = (int)(idx % a.d);
+            const size_t o = (size_t)i * a.dp + dd;
+            if (a.scratch_parts != nullptr) {
+                // reduce-scatter of the column gradient as this kernel's load phase: the local rows of every rank's accumulator
+                const size_t og = (size_t)(a.row_offset + i) * a.dp + dd;
+                float g = 0.0f;
+                for (int p0 = 0; p0 < a.n_ranks; p0 += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        v[k] = (p0 + k < a.n_ranks)
+                                   ? *reinterpret_cast<const volatile float*>(static_cast<const char*>(a.scratch_parts[p0 + k]) + a.g_off + og * sizeof(float))
+                                   : 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) g += v[k];
+                }
+                g *= -kTwoLn2;
+                if (a.gk != nullptr) g += a.gk[i] * a.mu_all[(int64_t)i * a.ldmu + dd];      // mu_all = this rank's rows here
+                a.grad_mu[(int64_t)i * a.ldgmu + dd] = g;
+            }
+            float sa = 0.0f, sc = 0.0f;
+            // partial slots of this (slice, row block): one per segment that touches the block
+            const int64_t qb = (int64_t)(dd / a.slice_dp) * a.n_rb + i / a.rows_per_block;
+            const int n_slots = seg_slots(a.seg, qb, a.tiles_per_block);
+            for (int s0 = 0; s0 < n_slots; s0 += 4) {
+                float va[4], vc[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool ok = s0 + k < n_slots;
+                    va[k] = ok ? __ldg(a.Apart + (size_t)(s0 + k) * split_stride + o) : 0.0f;
+                    vc[k] = ok ? __ldg(a.CRpart + (size_t)(s0 + k) * split_stride + o) : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { sa += va[k]; sc += vc[k]; }
+            }
+            float glv = a.vr[o] * (kTwoLn2 * sc);                         // the sweep accumulates sum r (c - 1/(2 ln2))
+            if (a.gk != nullptr) glv += a.gk[i] * 0.5f * (expf(a.lv[(int64_t)i * a.ldlv + dd]) - 1.0f);
+            a.grad_z[(int64_t)i * a.ldgz + dd] = kTwoLn2 * a.ns[o] * sa;
+            a.grad_lv[(int64_t)i * a.ldglv + dd] = glv;
+        } else {
+            const int64_t k = idx - n_row;
+            const int j = (int)(k / a.d), dd = (int)(k % a.d);
+            float g = -kTwoLn2 * a.Gpart[(size_t)j * a.dp + dd];
+            const int i = j - a.row_offset;
+            if (a.gk != nullptr && i >= 0 && i < a.b_loc) g += a.gk[i] * a.mu_all[(int64_t)j * a.ldmu + dd];
+            a.grad_mu[(int64_t)j * a.ldgmu + dd] = g;
         }
     }
-    if (p.dp == 64) return launch_bwd_ds_t<6, 2, 8, 2, 16>(p, a, fin, st);
-    return launch_bwd_ds_t<6, 1, 8, 2, 16>(p, a, fin, st);
+}
+
+// variant 0 is the shipped configuration; the others are tuning points kept for tools/tune_bwd.py (profiles/r2_bwd_ds_sweep.md)
+static cudaError_t launch_bwd_ds(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* fin, int variant, cudaStream_t st) {
+    if (p.dp >= 128) {
+        switch (variant) {
+            case 1:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 8>(p, a, fin, st);               // 12 rows/warp, 16 warps/SM, mask by multiply
+            case 2:  return launch_bwd_ds_t<8, 4, 12, 1, 16, 4>(p, a, fin, st);              // 4 columns per basic block, mask by multiply
+            case 3:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 4, true>(p, a, fin, st);         // two columns in lockstep
+            case 4:  return launch_bwd_ds_t<5, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);  // 10 rows/warp, 16 warps/SM
+            case 5:  return launch_bwd_ds_t<8, 4, 12, 1, 16, 16, false, true>(p, a, fin, st);  // the whole tile in one basic block
+            case 6:  return launch_bwd_ds_t<8, 4, 12, 1, 32, 8, false, true>(p, a, fin, st);   // 32-column tiles
+            case 7:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);
+            case 8:  return launch_bwd_ds_t<4, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);
+            case 9:  return launch_bwd_ds_t<9, 4, 12, 1, 16, 8, false, true>(p, a, fin, st);   // 18 rows/warp
+            case 10: return launch_bwd_ds_t<7, 4, 12, 1, 16, 8, false, true>(p, a, fin, st);   // 14 rows/warp
+            case 11: return launch_bwd_ds_t<8, 4, 12, 1, 16, 8>(p, a, fin, st);                // mask by multiply
+            case 12: return launch_bwd_ds_t<10, 4, 8, 1, 16, 8, false, true>(p, a, fin, st);   // 20 rows/warp, 8 warps/SM, 255 regs
+            default: return launch_bwd_ds_t<8, 4, 12, 1, 16, 8, false, true>(p, a, fin, st);   // 16 rows/warp, 12 warps/SM (168 regs),
+        }                                                                                       // 8 columns per basic block, mask by select
+    }
+    if (p.dp == 64) return launch_bwd_ds_t<8, 2, 12, 1, 16, 8, false, true>(p, a, fin, st);
+    return launch_bwd_ds_t<8, 1, 12, 1, 16, 8, false, true>(p, a, fin, st);
+}
+
+
+static int g_bwd_variant = 0;       // 0: shipped configuration; set through tcelbo_set_tuning("bwd_variant", v) by tools/tune_bwd.py
+void set_bwd_variant(int v) { g_bwd_variant = v < 0 ? 0 : v; }
+
+cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* fin, cudaStream_t st) {
+    return launch_bwd_ds(p, a, fin, g_bwd_variant, st);
+}
+
+cudaError_t launch_bwd_fused_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st) {
+    const int64_t n = (int64_t)p.b_loc * p.d + (int64_t)p.b_glob * p.d;
+    int64_t g = (n + 255) / 256; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1;
+    LaunchScope scope(kKernNone, st);
+    bwd_fused_finalize_kernel<<<(int)g, 256, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 }  // namespace tcelbo

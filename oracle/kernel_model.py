@@ -109,7 +109,7 @@ def backward_rowvar(fw, g_log_qz, g_log_qz_prod):
 
 
 def backward_rowvar_sweep(fw, g_log_qz, g_log_qz_prod):
-    """The same gradients with the fused sweep's own arithmetic (csrc/tc_bwd_fused.cu: bwd_pairs): the exponent is carried
+    """The same gradients with the fused sweep's own arithmetic (csrc/tc_bwd_ds.cu: ds_column): the exponent is carried
     shifted, q' = dl^2 - 1/(2 ln2), so that 2 ln2 qc - 1 = 2 ln2 qc' and the logvar sum is sum_j r qc'; e is recomputed as
     2^-qc' = e * exp(1/2) with the exp(-1/2) folded into gP/S."""
     p = fw["pro"]

@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = lambda *a: os.path.join(ROOT, "profiles", *a)      # noqa: E731
 
-IN_STEP = ("reparam_fwd", "col_prep", "row_prep", "tc_fwd_kernel", "fwd_finalize", "reduce_kernel", "bwd_prep", "tc_bwd_fused",
+IN_STEP = ("reparam_fwd", "col_prep", "row_prep", "tc_fwd_kernel", "fwd_finalize", "reduce_kernel", "bwd_prep", "tc_bwd_ds",
            "bwd_fused_finalize", "reparam_bwd_kernel<1>")
 
 
@@ -43,10 +43,10 @@ def main():
     out.append("")
     out.append(f"Shares from live CUDA events inside `bench.py` on the same build (graph replay, `r1_bench_n1.json`): forward sweep "
                f"{km['tc_fwd_kernel']:.3f} ms ({100 * km['tc_fwd_kernel'] / j['ms_per_step']:.1f} % of the {j['ms_per_step']:.3f} ms step), "
-               f"fused backward sweep {km['tc_bwd_fused_kernel']:.3f} ms ({100 * km['tc_bwd_fused_kernel'] / j['ms_per_step']:.1f} %) — the "
+               f"fused backward sweep {km['tc_bwd_ds_kernel']:.3f} ms ({100 * km['tc_bwd_ds_kernel'] / j['ms_per_step']:.1f} %) — the "
                "ncu launch list agrees.  `FillFunctor<unsigned char>` is bench.py's 256 MiB L2 flush between timed steps (outside the "
                "event pairs).\n")
-    out.append("## Full capture (`ncu --set full --clock-control none --import-source on -k regex:tc_fwd_kernel|tc_bwd_fused_kernel "
+    out.append("## Full capture (`ncu --set full --clock-control none --import-source on -k regex:tc_fwd_kernel|tc_bwd_ds_kernel "
                "--launch-skip 8 --launch-count 2`, same command; file `r1_ncu_full_final_raw.csv`)\n")
     out.append(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), P("r1_ncu_full_final_raw.csv")],
                               capture_output=True, text=True).stdout)
