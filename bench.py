@@ -222,12 +222,29 @@ def run_ours(args):
     eps = eps_h.to(dev)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
+    # the drop-in path: the reference's own call sequence -- reparameterize (ops.py:166), then the solver's
+    # compute_kl_loss(z, mu, logvar) with its default reduce="mean" (solvers/tc.py:58-89), then autograd's backward
+    from intro_tc_vae_b200.solvers import TCLossMixin
+
+    class _Dataset:
+        def __len__(self):
+            return N
+
+    class _Solver(TCLossMixin):
+        beta_kl = BETA
+        dataset = _Dataset()
+        process_group = group
+
+        def write_scalar(self, *a, **k):
+            pass
+
+    solver = _Solver()
+
     def step(mu_t, lv_t, eps_t):
         mu_t.grad = None
         lv_t.grad = None
         z = ops.reparameterize(mu_t, lv_t, eps_t)
-        # compute_kl_loss of solvers/tc.py:69-89 as one fused op (per-sample (beta-1)*tc + kl), mean-reduced
-        loss = ops.kl_tc_loss_terms(z, mu_t, lv_t, N, BETA, "mss", group)[0].mean()
+        loss = solver.compute_kl_loss(z, mu_t, lv_t)
         loss.backward()
         return loss
 
@@ -260,7 +277,7 @@ def run_ours(args):
         got = graphed.loss.item()
         assert abs(got - ref_loss) <= 1e-5 * abs(ref_loss), (got, ref_loss)
         graph_note = ("cuda-graph replay of" if not args.no_graph else "eager launches of") + \
-            " the whole step through the C ABI (reparameterize + fused loss forward + backward + reparameterize backward)"
+            " the whole step through the C ABI (tcelbo_klloss_forward_ex / _backward_ex: reparameterize and the batch mean fused, 6 launches)"
     except Exception as exc:                           # capture unsupported here: fall back to eager launches
         graphed = None
         graph_note = f"eager (graph capture failed: {type(exc).__name__}: {exc})"[:200]
@@ -271,6 +288,9 @@ def run_ours(args):
         graphed = None
     if graphed is None:
         exchange_note = "nccl" if world > 1 else "none"
+    if world > 1 and exchange_note == "peer":             # the drop-in solver gets its own symmetric buffers (collective construction)
+        from intro_tc_vae_b200.peer import PeerExchange
+        solver.peer_exchange = PeerExchange(b_loc, D, group, dev)
 
     def run_step():
         if graphed is not None:
@@ -340,6 +360,33 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(e_starts, e_stops))) / args.steps
     e2e_value = B * B * D / (e2e_ms * 1e-3)
+
+    # ---- the same two measurements through the DROP-IN path (eager: reparameterize -> solver.compute_kl_loss -> backward)
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        barrier()
+        a0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        a1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for k in range(args.steps):
+            flush_buf.fill_(k & 0xFF)
+            a0[k].record()
+            fn()
+            a1[k].record()
+        barrier()
+        return max_over_ranks(sum(x.elapsed_time(y) for x, y in zip(a0, a1))) / args.steps
+
+    def dropin_e2e_step():
+        mu_d = mu_h.to(dev, non_blocking=True).requires_grad_(True)
+        lv_d = lv_h.to(dev, non_blocking=True).requires_grad_(True)
+        eps_d = eps_h.to(dev, non_blocking=True)
+        loss = step(mu_d, lv_d, eps_d)
+        gmu_h.copy_(mu_d.grad, non_blocking=True)
+        glv_h.copy_(lv_d.grad, non_blocking=True)
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    dropin_ms = timed(lambda: step(mu, lv, eps))
+    dropin_e2e_ms = timed(dropin_e2e_step)
     t_region_end = time.perf_counter()
     if rank == 0:
         time.sleep(0.2)
@@ -447,6 +494,11 @@ def run_ours(args):
                                     "peer": "library kernels over NVLink peer memory (symmetric memory + 2 barriers)"}[exchange_note]},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 3 * b_loc * D * 4, "d2h_bytes_per_step": 2 * b_loc * D * 4 + 4},
+            "dropin": {"what": "same step through the reference's signatures: ops.reparameterize -> TCLossMixin.compute_kl_loss(z, mu, logvar) "
+                               "-> loss.backward(), eager launches, inputs resident in HBM",
+                       "ms_per_step": dropin_ms, "value": B * B * D / (dropin_ms * 1e-3), "unit": UNIT},
+            "e2e_dropin": {"value": B * B * D / (dropin_e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": dropin_e2e_ms,
+                           "h2d_bytes_per_step": 3 * b_loc * D * 4, "d2h_bytes_per_step": 2 * b_loc * D * 4 + 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

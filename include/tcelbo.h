@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define TCELBO_VERSION 1
+#define TCELBO_VERSION 2
 
 /* flags */
 #define TCELBO_EST_MSS            0u   /* minibatch stratified sampling (active in the reference) */
@@ -124,6 +124,40 @@ int tcelbo_klloss_backward(const float* z, int64_t ldz, const float* mu_all, int
                            const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
                            float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
                            const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream);
+
+/*
+ * Optional fusions around the fused loss; a NULL member switches its fusion off, a NULL struct all of them.
+ *   prologue  reparameterize, ops.py:183-185: with `eps` set, z is NOT read (pass NULL); z = mu + eps * exp(logvar / 2) of this
+ *             rank's rows is formed inside the prologue kernel and, if z_out != NULL, stored there for the decoder.  The
+ *             backward (same `eps`) then applies the chain rule through z itself: grad_logvar and this rank's rows of
+ *             grad_mu_all are the gradients w.r.t. the ENCODER outputs; grad_z still receives dLoss/dz.
+ *   epilogue  batch means, solvers/tc.py:83-89 with reduce="mean": loss_mean[0] = mean_i loss_rows[i], kl_mean[0] likewise
+ *             (mean over this rank's b_loc rows, summed in a fixed order);
+ *             soft-intro exp-ELBO term, solvers/intro.py:102-103 with kl_i = loss_rows[i] (solvers/intro.py:84-89):
+ *             e_rows[i] = exp(-2 * scale * (rec_rows[i] + loss_rows[i])), expelbo[0] = mean_i e_rows[i].
+ *   backward  g_loss_mean / g_kl_mean / g_expelbo are DEVICE scalars (dLoss/d of the three means); e_rows is the forward's;
+ *             g_rec_rows [b_loc] (optional output) receives dLoss/drec_rows[i] = g_expelbo * (-2 scale / b_loc) * e_rows[i].
+ */
+typedef struct tcelbo_fusion {
+    const float* eps; int64_t ldeps;
+    float* z_out; int64_t ldz_out;
+    float* loss_mean; float* kl_mean;
+    const float* rec_rows; float scale; float* expelbo; float* e_rows;
+    const float* g_loss_mean; const float* g_kl_mean; const float* g_expelbo; float* g_rec_rows;
+} tcelbo_fusion;
+
+/* tcelbo_klloss_forward / _backward with the fusions above; every per-row upstream gradient of the backward may be NULL as long
+ * as one upstream gradient (per-row or scalar) is given. */
+int tcelbo_klloss_forward_ex(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                             int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags, float beta,
+                             float* loss_rows, float* kl_rows, float* log_qz, float* log_qz_prod, const tcelbo_fusion* fusion,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int tcelbo_klloss_backward_ex(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                              int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags, float beta,
+                              const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
+                              const tcelbo_fusion* fusion,
+                              float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
+                              const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream);
 
 /*
  * Peer-memory exchange for the row-sharded fused loss (one process per GPU).  Replaces the NCCL all-gather of

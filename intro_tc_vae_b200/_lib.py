@@ -24,6 +24,15 @@ ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 1, 2, 3, 4
 
 _f = c_void_p          # device pointers are passed as integers (tensor.data_ptr())
 
+
+class Fusion(ctypes.Structure):
+    """``tcelbo_fusion`` of include/tcelbo.h: optional prologue / epilogue fusions of the fused loss (None = off)."""
+    _fields_ = [("eps", c_void_p), ("ldeps", c_int64), ("z_out", c_void_p), ("ldz_out", c_int64),
+                ("loss_mean", c_void_p), ("kl_mean", c_void_p),
+                ("rec_rows", c_void_p), ("scale", c_float), ("expelbo", c_void_p), ("e_rows", c_void_p),
+                ("g_loss_mean", c_void_p), ("g_kl_mean", c_void_p), ("g_expelbo", c_void_p), ("g_rec_rows", c_void_p)]
+
+
 _SIGNATURES = {
     "tcelbo_version": (c_int, []),
     "tcelbo_last_error": (c_char_p, []),
@@ -39,6 +48,11 @@ _SIGNATURES = {
     "tcelbo_klloss_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64, c_uint32, c_float,
                                        _f, _f, _f, _f, _f, c_int64, _f, c_int64, _f, c_int64, c_void_p, c_size_t, c_void_p, c_size_t,
                                        c_void_p]),
+    "tcelbo_klloss_forward_ex": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64, c_uint32, c_float,
+                                         _f, _f, _f, _f, POINTER(Fusion), c_void_p, c_size_t, c_void_p]),
+    "tcelbo_klloss_backward_ex": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64, c_uint32, c_float,
+                                          _f, _f, _f, _f, POINTER(Fusion), _f, c_int64, _f, c_int64, _f, c_int64, c_void_p, c_size_t,
+                                          c_void_p, c_size_t, c_void_p]),
     "tcelbo_klloss_forward_peer": (c_int, [_f, c_int64, _f, c_int64, c_void_p, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64,
                                            c_uint32, c_float, _f, _f, _f, _f, c_void_p, c_size_t, c_void_p]),
     "tcelbo_klloss_backward_peer": (c_int, [c_int, _f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64, c_uint32,

@@ -83,13 +83,13 @@ bool aligned256(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 255u) 
 template <typename T> T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
 
 int check_common(const float* z, const float* mu_all, const float* logvar, int b_loc, int b_glob, int row_offset, int d,
-                 int64_t dataset_size, uint32_t flags, int64_t ldz, int64_t ldmu, int64_t ldlv) {
-    if (!z || !mu_all || !logvar) return fail(TCELBO_ERR_INVALID, "null input pointer");
+                 int64_t dataset_size, uint32_t flags, int64_t ldz, int64_t ldmu, int64_t ldlv, bool z_optional = false) {
+    if ((!z && !z_optional) || !mu_all || !logvar) return fail(TCELBO_ERR_INVALID, "null input pointer");
     if (b_loc < 1 || b_glob < 1 || d < 1) return fail(TCELBO_ERR_INVALID, "b_loc, b_glob and d must be positive");
     if (b_glob < 2 && !(flags & TCELBO_EST_MWS)) return fail(TCELBO_ERR_INVALID, "b_glob == 1: the stratified weight divides by B-1 (ZeroDivisionError at ops.py:44)");
     if (row_offset < 0 || (int64_t)row_offset + b_loc > b_glob) return fail(TCELBO_ERR_INVALID, "rows [row_offset, row_offset+b_loc) exceed b_glob");
     if (dataset_size < 1) return fail(TCELBO_ERR_INVALID, "dataset_size must be positive");
-    if (ldz < d || ldmu < d || ldlv < d) return fail(TCELBO_ERR_INVALID, "row pitch smaller than d");
+    if ((z && ldz < d) || ldmu < d || ldlv < d) return fail(TCELBO_ERR_INVALID, "row pitch smaller than d");
     if (d > 512) return fail(TCELBO_ERR_UNSUPPORTED, "d = %d > 512 is outside the built kernels", d);
     return TCELBO_OK;
 }
@@ -120,6 +120,7 @@ struct LossFusion {            // solvers/tc.py:83-89 folded into the finalize k
     float* loss_rows = nullptr; float* kl_rows = nullptr;                 // forward outputs
     const float* g_loss = nullptr; const float* g_kl = nullptr;           // backward inputs
     bool on = false;
+    tcelbo_fusion fz = {};                                                // optional prologue / epilogue fusions (tcelbo.h)
 };
 
 // Peer-memory exchange (tcelbo_*_peer): the column operand / the column accumulators live in n_ranks allocations that
@@ -136,8 +137,11 @@ static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_
                         int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags,
                         float* log_qz, float* log_qz_prod, const LossFusion& lf,
                         void* workspace, size_t workspace_bytes, void* stream, const Peers& peers = Peers()) {
-    if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv)) return rc;
+    if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv, lf.fz.eps != nullptr)) return rc;
     if (!log_qz || !log_qz_prod) return fail(TCELBO_ERR_INVALID, "null output pointer");
+    if (lf.fz.eps && (lf.fz.ldeps < d || (lf.fz.z_out && lf.fz.ldz_out < d))) return fail(TCELBO_ERR_INVALID, "eps / z_out row pitch smaller than d");
+    if (lf.fz.eps && (flags & TCELBO_VAR_COL)) return fail(TCELBO_ERR_UNSUPPORTED, "the fused reparameterize covers the row-variance density");
+    if (lf.fz.expelbo && (!lf.fz.rec_rows || !lf.fz.e_rows)) return fail(TCELBO_ERR_INVALID, "expelbo needs rec_rows and e_rows");
     if (peers.on() && (flags & TCELBO_VAR_COL)) return fail(TCELBO_ERR_UNSUPPORTED, "the peer-memory exchange covers the row-variance density");
     Plan p;
     if (!make_plan(p, b_loc, b_glob, d, flags, sm_count())) return fail(TCELBO_ERR_INVALID, "cannot plan this shape");
@@ -157,13 +161,21 @@ static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_
     float* Spart = at<float>(workspace, p.off_scratch);
     float* Jpart = Spart + (size_t)p.n_part_fwd * p.bl_pad * p.dp;
 
+    const tcelbo_fusion& fz = lf.fz;
+    unsigned int* ticket = at<unsigned int>(workspace, p.off_red) + 3 * (size_t)p.n_fin_ctas;
     if (p.var_col) {
         if ((e = launch_colvar_prep(z, ldz, mu_all, ldmu, logvar, ldlv, p, mu_pad, zs, shift, st)) != cudaSuccess) return fail_cuda(e, "colvar_prep");
     } else {
-        if (peers.on()) {
-            if ((e = launch_col_prep_parts(peers.mu_parts, peers.ld_part, b_loc, p, mu_pad, st)) != cudaSuccess) return fail_cuda(e, "col_prep_parts");
-        } else if ((e = launch_col_prep(mu_all, ldmu, p, mu_pad, st)) != cudaSuccess) return fail_cuda(e, "col_prep");
-        if ((e = launch_row_prep(z, ldz, logvar, ldlv, p, zs, ns, qmax, shift, vr, st)) != cudaSuccess) return fail_cuda(e, "row_prep");
+        PrepArgs pa;
+        pa.mu_all = mu_all; pa.ldmu = ldmu;
+        pa.parts = peers.on() ? peers.mu_parts : nullptr; pa.ld_part = peers.ld_part; pa.rows_per_part = b_loc;
+        pa.z = z; pa.ldz = ldz;
+        pa.eps = fz.eps; pa.ldeps = fz.ldeps; pa.z_out = fz.z_out; pa.ldz_out = fz.ldz_out;
+        pa.mu_loc = peers.on() ? mu_all : mu_all + (int64_t)row_offset * ldmu; pa.ldmu_loc = ldmu;
+        pa.logvar = logvar; pa.ldlv = ldlv;
+        pa.b_loc = b_loc; pa.b_glob = b_glob; pa.d = d; pa.bl_pad = p.bl_pad; pa.bg_pad = p.bg_pad; pa.dp = p.dp;
+        pa.mu_pad = mu_pad; pa.zs = zs; pa.ns = ns; pa.qmax = qmax; pa.shift = shift; pa.vr = vr; pa.ticket = ticket;
+        if ((e = launch_prep(pa, st)) != cudaSuccess) return fail_cuda(e, "prep");
     }
 
     FwdArgs fa;
@@ -188,9 +200,16 @@ static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_
     fin.seg = p.seg_fwd; if (p.var_col) fin.seg.n_ctas = 0;
     fin.tiles_per_block = p.tiles_fwd; fin.rows_per_block = p.fwd_rows;
     fin.lv = nullptr; fin.ldlv = 0; fin.mu_loc = nullptr; fin.ldmu = 0; fin.beta = lf.beta; fin.loss_rows = nullptr; fin.kl_rows = nullptr;
+    fin.loss_mean = nullptr; fin.kl_mean = nullptr; fin.rec_rows = nullptr; fin.scale = 0.0f; fin.expelbo = nullptr; fin.e_rows = nullptr;
+    fin.red_part = nullptr; fin.ticket = nullptr;
     if (lf.on) {
         fin.lv = logvar; fin.ldlv = ldlv; fin.mu_loc = peers.on() ? mu_all : mu_all + (int64_t)row_offset * ldmu; fin.ldmu = ldmu;
         fin.loss_rows = lf.loss_rows; fin.kl_rows = lf.kl_rows;
+        if (fz.loss_mean || fz.kl_mean || fz.expelbo) {
+            fin.loss_mean = fz.loss_mean; fin.kl_mean = fz.kl_mean;
+            fin.red_part = at<float>(workspace, p.off_red); fin.ticket = ticket;
+        }
+        if (fz.expelbo) { fin.rec_rows = fz.rec_rows; fin.scale = fz.scale; fin.expelbo = fz.expelbo; fin.e_rows = fz.e_rows; }
     }
     if ((e = launch_fwd_finalize(p, fin, st)) != cudaSuccess) return fail_cuda(e, "fwd_finalize");
     return TCELBO_OK;
@@ -202,8 +221,10 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
                          float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
                          const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream,
                          const Peers& peers = Peers()) {
-    if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv)) return rc;
+    if (int rc = check_common(z, mu_all, logvar, b_loc, b_glob, row_offset, d, dataset_size, flags, ldz, ldmu, ldlv, true)) return rc;
     if (peers.on() && (flags & TCELBO_VAR_COL)) return fail(TCELBO_ERR_UNSUPPORTED, "the peer-memory exchange covers the row-variance density");
+    if (lf.fz.eps && lf.fz.ldeps < d) return fail(TCELBO_ERR_INVALID, "eps row pitch smaller than d");
+    if (lf.fz.g_expelbo && !lf.fz.e_rows) return fail(TCELBO_ERR_INVALID, "g_expelbo needs the e_rows the forward wrote");
     if (!(flags & TCELBO_SAVE_FOR_BACKWARD)) return fail(TCELBO_ERR_INVALID, "backward needs the workspace of a forward run with TCELBO_SAVE_FOR_BACKWARD");
     if (!grad_z || !grad_mu_all || !grad_logvar) return fail(TCELBO_ERR_INVALID, "null gradient pointer");
     if (!lf.on && (!g_log_qz || !g_log_qz_prod)) return fail(TCELBO_ERR_INVALID, "null upstream gradient pointer");
@@ -236,8 +257,12 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
     float* Gpart = at<float>(scratch, p.boff_G);
 
     const size_t zero_n = (size_t)(p.var_col ? 2 : 1) * p.bg_pad * p.dp;
-    if ((peers.phase & 1) && (e = launch_bwd_prep(p, g_log_qz, g_log_qz_prod, lf.g_loss, lf.g_kl, lf.beta, S, gps, gj, lf.on ? gk : nullptr,
-                             Gpart, zero_n, st)) != cudaSuccess) return fail_cuda(e, "bwd_prep");
+    BwdUpstream up;
+    up.g_log_qz = g_log_qz; up.g_log_qz_prod = g_log_qz_prod; up.g_loss = lf.g_loss; up.g_kl = lf.g_kl;
+    up.g_loss_mean = lf.fz.g_loss_mean; up.g_kl_mean = lf.fz.g_kl_mean; up.g_expelbo = lf.fz.g_expelbo; up.e_rows = lf.fz.e_rows;
+    up.scale = lf.fz.scale; up.g_rec_rows = lf.fz.g_rec_rows; up.beta = lf.beta;
+    if ((peers.phase & 1) && (e = launch_bwd_prep(p, up, S, gps, gj, lf.on ? gk : nullptr, Gpart, zero_n, st)) != cudaSuccess)
+        return fail_cuda(e, "bwd_prep");
 
     BwdFinArgs fa;
     fa.Apart = Apart; fa.CRpart = CRpart; fa.Gpart = Gpart; fa.ns = ns; fa.vr = vr;
@@ -247,6 +272,7 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
     fa.seg = Segments{0, 0, 0}; fa.tiles_per_block = 0; fa.n_rb = 0; fa.rows_per_block = 0; fa.slice_dp = 0;
     fa.gk = lf.on ? gk : nullptr; fa.lv = logvar; fa.ldlv = ldlv; fa.mu_all = mu_all; fa.ldmu = ldmu; fa.row_offset = row_offset;
     fa.scratch_parts = peers.on() ? peers.scratch_parts : nullptr; fa.g_off = p.boff_G; fa.n_ranks = peers.n_ranks;
+    fa.eps = lf.fz.eps; fa.ldeps = lf.fz.ldeps;
 
     BwdFusedArgs ua;
     ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
@@ -303,6 +329,32 @@ int tcelbo_klloss_backward(const float* z, int64_t ldz, const float* mu_all, int
                            const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream) {
     if (!g_loss_rows) return fail(TCELBO_ERR_INVALID, "null upstream gradient pointer");
     LossFusion lf; lf.on = true; lf.beta = beta; lf.g_loss = g_loss_rows; lf.g_kl = g_kl_rows;
+    return backward_impl(z, ldz, mu_all, ldmu, logvar, ldlv, b_loc, b_glob, row_offset, d, dataset_size, flags,
+                         g_log_qz, g_log_qz_prod, lf, grad_z, ldgz, grad_mu_all, ldgmu, grad_logvar, ldglv,
+                         workspace, workspace_bytes, scratch, scratch_bytes, stream);
+}
+
+int tcelbo_klloss_forward_ex(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                             int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags, float beta,
+                             float* loss_rows, float* kl_rows, float* log_qz, float* log_qz_prod, const tcelbo_fusion* fusion,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    if (!loss_rows || !kl_rows) return fail(TCELBO_ERR_INVALID, "null output pointer");
+    LossFusion lf; lf.on = true; lf.beta = beta; lf.loss_rows = loss_rows; lf.kl_rows = kl_rows;
+    if (fusion) lf.fz = *fusion;
+    return forward_impl(z, ldz, mu_all, ldmu, logvar, ldlv, b_loc, b_glob, row_offset, d, dataset_size, flags,
+                        log_qz, log_qz_prod, lf, workspace, workspace_bytes, stream);
+}
+
+int tcelbo_klloss_backward_ex(const float* z, int64_t ldz, const float* mu_all, int64_t ldmu, const float* logvar, int64_t ldlv,
+                              int b_loc, int b_glob, int row_offset, int d, int64_t dataset_size, uint32_t flags, float beta,
+                              const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
+                              const tcelbo_fusion* fusion,
+                              float* grad_z, int64_t ldgz, float* grad_mu_all, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
+                              const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes, void* stream) {
+    LossFusion lf; lf.on = true; lf.beta = beta; lf.g_loss = g_loss_rows; lf.g_kl = g_kl_rows;
+    if (fusion) lf.fz = *fusion;
+    if (!g_loss_rows && !lf.fz.g_loss_mean && !lf.fz.g_expelbo && !g_kl_rows && !lf.fz.g_kl_mean && !g_log_qz && !g_log_qz_prod)
+        return fail(TCELBO_ERR_INVALID, "no upstream gradient given");
     return backward_impl(z, ldz, mu_all, ldmu, logvar, ldlv, b_loc, b_glob, row_offset, d, dataset_size, flags,
                          g_log_qz, g_log_qz_prod, lf, grad_z, ldgz, grad_mu_all, ldgmu, grad_logvar, ldglv,
                          workspace, workspace_bytes, scratch, scratch_bytes, stream);

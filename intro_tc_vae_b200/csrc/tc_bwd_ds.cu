@@ -384,28 +384,11 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
     const int64_t n_row = (int64_t)a.b_loc * a.d;
     const int64_t n_col = a.scratch_parts != nullptr ? 0 : (int64_t)a.b_glob * a.d;
     const size_t split_stride = (size_t)a.bl_pad * a.dp;
+    const bool rows_own_mu = a.scratch_parts != nullptr || a.eps != nullptr;   // the row threads also write grad_mu of the local rows
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_row + n_col; idx += (int64_t)gridDim.x * blockDim.x) {
         if (idx < n_row) {
             const int i = (int)(idx / a.d), dd = (int)(idx % a.d);
             const size_t o = (size_t)i * a.dp + dd;
-            if (a.scratch_parts != nullptr) {
-                // reduce-scatter of the column gradient as this kernel's load phase: the local rows of every rank's accumulator
-                const size_t og = (size_t)(a.row_offset + i) * a.dp + dd;
-                float g = 0.0f;
-                for (int p0 = 0; p0 < a.n_ranks; p0 += 8) {
-                    float v[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        v[k] = (p0 + k < a.n_ranks)
-                                   ? *reinterpret_cast<const volatile float*>(static_cast<const char*>(a.scratch_parts[p0 + k]) + a.g_off + og * sizeof(float))
-                                   : 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) g += v[k];
-                }
-                g *= -kTwoLn2;
-                if (a.gk != nullptr) g += a.gk[i] * a.mu_all[(int64_t)i * a.ldmu + dd];      // mu_all = this rank's rows here
-                a.grad_mu[(int64_t)i * a.ldgmu + dd] = g;
-            }
             float sa = 0.0f, sc = 0.0f;
             // partial slots of this (slice, row block): one per segment that touches the block
             const int64_t qb = (int64_t)(dd / a.slice_dp) * a.n_rb + i / a.rows_per_block;
@@ -422,15 +405,46 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
                 for (int k = 0; k < 4; ++k) { sa += va[k]; sc += vc[k]; }
             }
             float glv = a.vr[o] * (kTwoLn2 * sc);                         // the sweep accumulates sum r (c - 1/(2 ln2))
-            if (a.gk != nullptr) glv += a.gk[i] * 0.5f * (expf(a.lv[(int64_t)i * a.ldlv + dd]) - 1.0f);
-            a.grad_z[(int64_t)i * a.ldgz + dd] = kTwoLn2 * a.ns[o] * sa;
+            const float lv = (a.gk != nullptr || a.eps != nullptr) ? a.lv[(int64_t)i * a.ldlv + dd] : 0.0f;
+            if (a.gk != nullptr) glv += a.gk[i] * 0.5f * (expf(lv) - 1.0f);
+            const float gz = kTwoLn2 * a.ns[o] * sa;
+            if (a.eps != nullptr) glv += gz * a.eps[(int64_t)i * a.ldeps + dd] * (0.5f * expf(0.5f * lv));    // through z = mu + eps*std
+            a.grad_z[(int64_t)i * a.ldgz + dd] = gz;
             a.grad_lv[(int64_t)i * a.ldglv + dd] = glv;
+            if (rows_own_mu) {
+                const size_t og = (size_t)(a.row_offset + i) * a.dp + dd;
+                float g = 0.0f;
+                if (a.scratch_parts != nullptr) {
+                    // reduce-scatter of the column gradient as this kernel's load phase: the local rows of every rank's accumulator
+                    for (int p0 = 0; p0 < a.n_ranks; p0 += 8) {
+                        float v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            v[k] = (p0 + k < a.n_ranks)
+                                       ? *reinterpret_cast<const volatile float*>(static_cast<const char*>(a.scratch_parts[p0 + k]) + a.g_off + og * sizeof(float))
+                                       : 0.0f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) g += v[k];
+                    }
+                } else {
+                    g = a.Gpart[og];
+                }
+                g *= -kTwoLn2;
+                // mu_all holds this rank's rows only in the peer mode, all rows otherwise
+                const int64_t mrow = a.scratch_parts != nullptr ? i : a.row_offset + i;
+                if (a.gk != nullptr) g += a.gk[i] * a.mu_all[mrow * a.ldmu + dd];
+                if (a.eps != nullptr) g += gz;
+                const int64_t grow = a.scratch_parts != nullptr ? i : a.row_offset + i;     // grad_mu covers the local rows only in the peer mode
+                a.grad_mu[grow * a.ldgmu + dd] = g;
+            }
         } else {
             const int64_t k = idx - n_row;
             const int j = (int)(k / a.d), dd = (int)(k % a.d);
-            float g = -kTwoLn2 * a.Gpart[(size_t)j * a.dp + dd];
             const int i = j - a.row_offset;
-            if (a.gk != nullptr && i >= 0 && i < a.b_loc) g += a.gk[i] * a.mu_all[(int64_t)j * a.ldmu + dd];
+            const bool local = i >= 0 && i < a.b_loc;
+            if (local && rows_own_mu) continue;
+            float g = -kTwoLn2 * a.Gpart[(size_t)j * a.dp + dd];
+            if (a.gk != nullptr && local) g += a.gk[i] * a.mu_all[(int64_t)j * a.ldmu + dd];
             a.grad_mu[(int64_t)j * a.ldgmu + dd] = g;
         }
     }

@@ -19,54 +19,51 @@ namespace tcelbo {
 // =====================================================================================================
 // Prologues: pad/copy the column operand, derive the per-(i,d) constants
 // =====================================================================================================
-__global__ void col_prep_kernel(const float* __restrict__ mu_all, int64_t ldmu, int b_glob, int d,
-                                int bg_pad, int dp, float* __restrict__ mu_pad) {
-    const int64_t n = (int64_t)bg_pad * dp;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int j = (int)(idx / dp), dd = (int)(idx % dp);
-        mu_pad[idx] = (j < b_glob && dd < d) ? mu_all[(int64_t)j * ldmu + dd] : 0.0f;
-    }
-}
-
-// Same, with the rows of mu living in `rows_per_part`-row blocks of different allocations (one per rank, peer-mapped):
-// the all-gather of the column operand is this kernel's load phase (coalesced 128-byte reads over NVLink).
-__global__ void col_prep_parts_kernel(const float* const* __restrict__ parts, int64_t ld_part, int rows_per_part, int b_glob, int d,
-                                      int bg_pad, int dp, float* __restrict__ mu_pad) {
-    const int64_t n = (int64_t)bg_pad * dp;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int j = (int)(idx / dp), dd = (int)(idx % dp);
-        float v = 0.0f;
-        if (j < b_glob && dd < d) {
-            const int part = j / rows_per_part;
-            v = *static_cast<const volatile float*>(parts[part] + (int64_t)(j - part * rows_per_part) * ld_part + dd);   // no L1 / nc path
+template <bool kParts>
+__global__ void prep_kernel(const PrepArgs a) {
+    const int64_t n_col = (int64_t)a.bg_pad * a.dp, n_row = (int64_t)a.bl_pad * a.dp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket = 0u;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_col + n_row; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (idx < n_col) {
+            // column operand, padded; with kParts the rows of mu live in `rows_per_part`-row blocks of different allocations (one
+            // per rank, peer-mapped): the all-gather of the column operand is this kernel's load phase (128-byte reads over NVLink)
+            const int j = (int)(idx / a.dp), dd = (int)(idx % a.dp);
+            float v = 0.0f;
+            if (j < a.b_glob && dd < a.d) {
+                if (kParts) {
+                    const int part = j / a.rows_per_part;
+                    v = *static_cast<const volatile float*>(a.parts[part] + (int64_t)(j - part * a.rows_per_part) * a.ld_part + dd);   // no L1 / nc path
+                } else {
+                    v = a.mu_all[(int64_t)j * a.ldmu + dd];
+                }
+            }
+            a.mu_pad[idx] = v;
+        } else {
+            const int64_t k = idx - n_col;
+            const int i = (int)(k / a.dp), dd = (int)(k % a.dp);
+            float o_zs = 0.f, o_ns = 0.f, o_q = 0.f, o_sh = 0.f, o_vr = 0.f;
+            if (i < a.b_loc && dd < a.d) {
+                const float lv = a.logvar[(int64_t)i * a.ldlv + dd];
+                float zv;
+                if (a.eps != nullptr) {                                     // fused reparameterize, ops.py:183-185
+                    zv = a.mu_loc[(int64_t)i * a.ldmu_loc + dd] + a.eps[(int64_t)i * a.ldeps + dd] * expf(0.5f * lv);
+                    if (a.z_out != nullptr) a.z_out[(int64_t)i * a.ldz_out + dd] = zv;
+                } else {
+                    zv = a.z[(int64_t)i * a.ldz + dd];
+                }
+                const float var = expf(lv);
+                const float vc = (var < kVarFloor) ? kVarFloor : var;       // NaN stays NaN, like clamp_
+                const float iv = 1.0f / vc;
+                const float c = -0.5f * (logf(vc) + kLog2Pi);
+                const float sc = sqrtf(0.5f * kLog2e * iv);
+                o_zs = zv * sc;
+                o_ns = -sc;
+                o_q = fmaxf(0.0f, (50.0f + c) * kLog2e);
+                o_sh = (c < kLogpFloor) ? kLogpFloor : c;
+                o_vr = 0.5f * var * iv;                                     // straight-through floor: d/dlv uses the unclamped var
+            }
+            a.zs[k] = o_zs; a.ns[k] = o_ns; a.qmax[k] = o_q; a.shift[k] = o_sh; a.vr[k] = o_vr;
         }
-        mu_pad[idx] = v;
-    }
-}
-
-__global__ void row_prep_kernel(const float* __restrict__ z, int64_t ldz, const float* __restrict__ logvar, int64_t ldlv,
-                                int b_loc, int d, int bl_pad, int dp,
-                                float* __restrict__ zs, float* __restrict__ ns, float* __restrict__ qmax,
-                                float* __restrict__ shift, float* __restrict__ vr) {
-    const int64_t n = (int64_t)bl_pad * dp;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)(idx / dp), dd = (int)(idx % dp);
-        float o_zs = 0.f, o_ns = 0.f, o_q = 0.f, o_sh = 0.f, o_vr = 0.f;
-        if (i < b_loc && dd < d) {
-            const float lv = logvar[(int64_t)i * ldlv + dd];
-            const float zv = z[(int64_t)i * ldz + dd];
-            const float var = expf(lv);
-            const float vc = (var < kVarFloor) ? kVarFloor : var;       // NaN stays NaN, like clamp_
-            const float iv = 1.0f / vc;
-            const float c = -0.5f * (logf(vc) + kLog2Pi);
-            const float s = sqrtf(0.5f * kLog2e * iv);
-            o_zs = zv * s;
-            o_ns = -s;
-            o_q = fmaxf(0.0f, (50.0f + c) * kLog2e);
-            o_sh = (c < kLogpFloor) ? kLogpFloor : c;
-            o_vr = 0.5f * var * iv;                                     // straight-through floor: d/dlv uses the unclamped var
-        }
-        zs[idx] = o_zs; ns[idx] = o_ns; qmax[idx] = o_q; shift[idx] = o_sh; vr[idx] = o_vr;
     }
 }
 
@@ -260,8 +257,10 @@ tc_fwd_kernel(const FwdArgs a) {
 // emit log_qz / log_qz_prod and, when asked, the fused KL and (beta-1)*TC + KL of solvers/tc.py:83-89.
 __global__ void fwd_finalize_kernel(const FinArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (row >= a.b_loc) return;
+    const int row_raw = blockIdx.x * (blockDim.x >> 5) + warp;
+    const bool row_ok = row_raw < a.b_loc;
+    if (!row_ok && a.red_part == nullptr) return;
+    const int row = row_ok ? row_raw : a.b_loc - 1;           // surplus warps of the last CTA recompute its last row and drop the result
     float P = 0.0f, C = 0.0f;
     const size_t split_stride = (size_t)a.bl_pad * a.dp;
     int n_js = a.n_js;                                     // uniform column split, or (balanced segments) the number of
@@ -279,7 +278,7 @@ __global__ void fwd_finalize_kernel(const FinArgs a) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
         }
-        *reinterpret_cast<float4*>(a.S + (size_t)row * a.dp + d0) = acc;
+        if (row_ok) *reinterpret_cast<float4*>(a.S + (size_t)row * a.dp + d0) = acc;
         const float4 sh = *reinterpret_cast<const float4*>(a.shift + (size_t)row * a.dp + d0);
         const float Sv[4] = {acc.x, acc.y, acc.z, acc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
@@ -300,7 +299,8 @@ __global__ void fwd_finalize_kernel(const FinArgs a) {
         C += __shfl_xor_sync(0xffffffffu, C, o);
         kl += __shfl_xor_sync(0xffffffffu, kl, o);
     }
-    if (lane == 0) {
+    float loss_i = 0.0f, kl_i = 0.0f, e_i = 0.0f;
+    if (lane == 0 && row_ok) {
         const float2* pj = reinterpret_cast<const float2*>(a.Jpart);
         float m = kNegBig, s = 0.0f;
         for (int k = 0; k < n_js; ++k) {
@@ -317,8 +317,47 @@ __global__ void fwd_finalize_kernel(const FinArgs a) {
         if (a.lv != nullptr) {
             kl *= -0.5f;
             a.kl_rows[row] = kl;
-            a.loss_rows[row] = (a.beta - 1.0f) * (lq - P) + kl;
+            loss_i = (a.beta - 1.0f) * (lq - P) + kl;
+            kl_i = kl;
+            a.loss_rows[row] = loss_i;
+            if (a.rec_rows != nullptr) {
+                e_i = expf(-2.0f * a.scale * (a.rec_rows[row] + loss_i));
+                a.e_rows[row] = e_i;
+            }
         }
+    }
+    if (a.red_part == nullptr) return;
+    // ---- batch means: per-CTA partials in a fixed slot, summed in fixed order by the last CTA to arrive (deterministic)
+    __shared__ float sh[3][kFinWarps];
+    __shared__ bool last;
+    if (lane == 0) { sh[0][warp] = loss_i; sh[1][warp] = kl_i; sh[2][warp] = e_i; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+        for (int w = 0; w < kFinWarps; ++w) { t0 += sh[0][w]; t1 += sh[1][w]; t2 += sh[2][w]; }
+        a.red_part[blockIdx.x] = t0; a.red_part[gridDim.x + blockIdx.x] = t1; a.red_part[2 * gridDim.x + blockIdx.x] = t2;
+        __threadfence();
+        last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last || warp != 0) return;
+    __threadfence();
+    float t[3] = {0.0f, 0.0f, 0.0f};
+    for (int k = lane; k < (int)gridDim.x; k += 32) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) t[q] += *(volatile float*)(a.red_part + q * gridDim.x + k);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) t[q] += __shfl_xor_sync(0xffffffffu, t[q], o);
+    }
+    if (lane == 0) {
+        const float inv_b = 1.0f / (float)a.b_loc;
+        if (a.loss_mean) a.loss_mean[0] = t[0] * inv_b;
+        if (a.kl_mean) a.kl_mean[0] = t[1] * inv_b;
+        if (a.expelbo) a.expelbo[0] = t[2] * inv_b;
+        *a.ticket = 0u;
     }
 }
 
@@ -330,30 +369,41 @@ __global__ void fwd_finalize_kernel(const FinArgs a) {
 // Thread mapping for both: the 32 lanes of a warp span the latent dims (VEC consecutive dims per lane
 // and chunk), so accumulators never cross lanes and no shuffles are needed.
 // =====================================================================================================
-__global__ void bwd_prep_kernel(const float* __restrict__ g_log_qz, const float* __restrict__ g_log_qz_prod,
-                                const float* __restrict__ g_loss, const float* __restrict__ g_kl, float beta,
-                                const float* __restrict__ S, int b_loc, int bl_pad, int dp,
+__global__ void bwd_prep_kernel(const BwdUpstream u, const float* __restrict__ S, int b_loc, int bl_pad, int dp,
                                 float* __restrict__ gps, float* __restrict__ gj, float* __restrict__ gk,
                                 float* __restrict__ zero, int64_t zero_n) {
     const int64_t n = (int64_t)bl_pad * dp;
     const int64_t total = n > zero_n ? n : zero_n;
+    const float inv_b = 1.0f / (float)b_loc;
+    const float gl_mean = u.g_loss_mean ? u.g_loss_mean[0] * inv_b : 0.0f;
+    const float gk_mean = u.g_kl_mean ? u.g_kl_mean[0] * inv_b : 0.0f;
+    const float ge = u.g_expelbo ? u.g_expelbo[0] * (-2.0f * u.scale * inv_b) : 0.0f;
+    auto g_loss_of = [&](int i, float& g_rec) {                 // dLoss/dloss_rows[i]; g_rec = its exp-ELBO part (= dLoss/drec_rows[i])
+        g_rec = u.g_expelbo ? ge * u.e_rows[i] : 0.0f;
+        return (u.g_loss ? u.g_loss[i] : 0.0f) + gl_mean + g_rec;
+    };
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         if (idx < zero_n) zero[idx] = 0.0f;
         if (idx >= n) continue;
         const int i = (int)(idx / dp);
         float gP = 0.0f;
         if (i < b_loc) {
-            if (g_log_qz_prod) gP += g_log_qz_prod[i];
-            if (g_loss) gP -= (beta - 1.0f) * g_loss[i];
+            float g_rec;
+            if (u.g_log_qz_prod) gP += u.g_log_qz_prod[i];
+            gP -= (u.beta - 1.0f) * g_loss_of(i, g_rec);
             gP /= S[idx];
         }
         gps[idx] = gP;
         if (idx < bl_pad) {
             float gJ = 0.0f, k = 0.0f;
             if (idx < b_loc) {
-                if (g_log_qz) gJ += g_log_qz[idx];
-                if (g_loss) { gJ += (beta - 1.0f) * g_loss[idx]; k += g_loss[idx]; }
-                if (g_kl) k += g_kl[idx];
+                float g_rec;
+                const float gl = g_loss_of((int)idx, g_rec);
+                if (u.g_log_qz) gJ += u.g_log_qz[idx];
+                gJ += (u.beta - 1.0f) * gl;
+                k = gl + gk_mean;
+                if (u.g_kl) k += u.g_kl[idx];
+                if (u.g_rec_rows) u.g_rec_rows[idx] = g_rec;
             }
             gj[idx] = gJ;
             if (gk) gk[idx] = k;
@@ -388,25 +438,11 @@ static cudaError_t launch_fwd_t(const Plan& p, const FwdArgs& a, cudaStream_t st
     return cudaGetLastError();
 }
 
-cudaError_t launch_col_prep(const float* mu_all, int64_t ldmu, const Plan& p, float* mu_pad, cudaStream_t st) {
-    const int64_t n = (int64_t)p.bg_pad * p.dp;
+cudaError_t launch_prep(const PrepArgs& a, cudaStream_t st) {
+    const int64_t n = ((int64_t)a.bg_pad + a.bl_pad) * a.dp;
     LaunchScope scope(kKernNone, st);
-    col_prep_kernel<<<grid_for(n, 256), 256, 0, st>>>(mu_all, ldmu, p.b_glob, p.d, p.bg_pad, p.dp, mu_pad);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_col_prep_parts(const float* const* parts, int64_t ld_part, int rows_per_part, const Plan& p, float* mu_pad, cudaStream_t st) {
-    const int64_t n = (int64_t)p.bg_pad * p.dp;
-    LaunchScope scope(kKernNone, st);
-    col_prep_parts_kernel<<<grid_for(n, 256), 256, 0, st>>>(parts, ld_part, rows_per_part, p.b_glob, p.d, p.bg_pad, p.dp, mu_pad);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_row_prep(const float* z, int64_t ldz, const float* logvar, int64_t ldlv, const Plan& p,
-                            float* zs, float* ns, float* qmax, float* shift, float* vr, cudaStream_t st) {
-    const int64_t n = (int64_t)p.bl_pad * p.dp;
-    LaunchScope scope(kKernNone, st);
-    row_prep_kernel<<<grid_for(n, 256), 256, 0, st>>>(z, ldz, logvar, ldlv, p.b_loc, p.d, p.bl_pad, p.dp, zs, ns, qmax, shift, vr);
+    if (a.parts != nullptr) prep_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(a);
+    else                    prep_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -422,19 +458,17 @@ cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st) {
-    const int warps = 8;
     LaunchScope scope(kKernNone, st);
-    fwd_finalize_kernel<<<(p.b_loc + warps - 1) / warps, warps * 32, 0, st>>>(a);
+    fwd_finalize_kernel<<<p.n_fin_ctas, kFinWarps * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g_log_qz_prod, const float* g_loss, const float* g_kl,
-                            float beta, const float* S, float* gps, float* gj, float* gk, float* zero, size_t zero_n, cudaStream_t st) {
+cudaError_t launch_bwd_prep(const Plan& p, const BwdUpstream& u, const float* S, float* gps, float* gj, float* gk,
+                            float* zero, size_t zero_n, cudaStream_t st) {
     const int64_t n = (int64_t)p.bl_pad * p.dp;
     const int64_t total = n > (int64_t)zero_n ? n : (int64_t)zero_n;
     LaunchScope scope(kKernNone, st);
-    bwd_prep_kernel<<<grid_for(total, 256), 256, 0, st>>>(g_log_qz, g_log_qz_prod, g_loss, g_kl, beta, S, p.b_loc, p.bl_pad, p.dp,
-                                                           gps, gj, gk, zero, (int64_t)zero_n);
+    bwd_prep_kernel<<<grid_for(total, 256), 256, 0, st>>>(u, S, p.b_loc, p.bl_pad, p.dp, gps, gj, gk, zero, (int64_t)zero_n);
     return cudaGetLastError();
 }
 

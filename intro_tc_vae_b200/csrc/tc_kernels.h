@@ -27,6 +27,24 @@ struct FinArgs {
     // optional fusion of solvers/tc.py:83-89: kl_i (ops.py:161-163) and loss_i = (beta-1)*(log_qz-log_qz_prod) + kl_i
     const float* lv; int64_t ldlv; const float* mu_loc; int64_t ldmu;   // this rank's rows of logvar / mu (nullptr: no fusion)
     float beta; float* loss_rows; float* kl_rows;
+    // optional batch-level epilogue, reduced deterministically by the last CTA to finish (fixed summation order):
+    //   loss_mean = mean_i loss_rows[i], kl_mean = mean_i kl_rows[i]               (solvers/tc.py:83-89 with reduce="mean")
+    //   e_rows[i] = exp(-2*scale*(rec_rows[i] + loss_rows[i])), expelbo = mean_i e_rows[i]   (solvers/intro.py:102-103)
+    float* loss_mean; float* kl_mean; const float* rec_rows; float scale; float* expelbo; float* e_rows;
+    float* red_part; unsigned int* ticket;                       // [3][gridDim.x] partial sums, arrival counter (zeroed by the prologue)
+};
+
+// One prologue kernel: pads / gathers the column operand, derives the per-(i,d) row constants, optionally forms
+// z = mu + eps * exp(logvar / 2) on the fly (ops.py:183-185), zeroes the finalize kernel's ticket.
+struct PrepArgs {
+    const float* mu_all; int64_t ldmu;                           // [b_glob][d] columns (ignored when parts != nullptr)
+    const float* const* parts; int64_t ld_part; int rows_per_part;   // peer exchange: one [rows_per_part][d] block per rank
+    const float* z; int64_t ldz;                                 // sampled latents of the local rows, or nullptr with eps set
+    const float* eps; int64_t ldeps; const float* mu_loc; int64_t ldmu_loc; float* z_out; int64_t ldz_out;
+    const float* logvar; int64_t ldlv;
+    int b_loc, b_glob, d, bl_pad, bg_pad, dp;
+    float* mu_pad; float* zs; float* ns; float* qmax; float* shift; float* vr;
+    unsigned int* ticket;
 };
 
 struct BwdFusedArgs {
@@ -56,19 +74,27 @@ struct BwdFinArgs {
     // peer-memory exchange: every rank's backward scratch (device table of n_ranks base pointers); the column sums of this
     // rank's rows are read straight from the peers' accumulators and grad_mu covers the local rows only (nullptr: grad_mu_all)
     const void* const* scratch_parts; size_t g_off; int n_ranks;
+    // fused reparameterize backward (ops.py:183-185): with eps set, the local rows of grad_mu also receive grad_z and grad_lv
+    // receives grad_z * eps * 0.5 * exp(logvar / 2), i.e. the outputs are the gradients w.r.t. the encoder's mu / logvar
+    const float* eps; int64_t ldeps;
 };
 
-cudaError_t launch_col_prep(const float* mu_all, int64_t ldmu, const Plan& p, float* mu_pad, cudaStream_t st);
-// column operand read from n_parts equal row blocks in different allocations (peer GPUs' memory mapped over NVLink)
-cudaError_t launch_col_prep_parts(const float* const* parts, int64_t ld_part, int rows_per_part, const Plan& p, float* mu_pad, cudaStream_t st);
-cudaError_t launch_row_prep(const float* z, int64_t ldz, const float* logvar, int64_t ldlv, const Plan& p,
-                            float* zs, float* ns, float* qmax, float* shift, float* vr, cudaStream_t st);
+cudaError_t launch_prep(const PrepArgs& a, cudaStream_t st);
 cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st);
 cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st);
-// gJ_i = g_log_qz[i] + (beta-1)*g_loss[i], gP_i = g_log_qz_prod[i] - (beta-1)*g_loss[i] (either input may be null);
-// writes gps = gP/S, gj = gJ, gk = g_loss + g_kl (if gk != null) and zeroes `zero_n` floats at `zero` (the column accumulator).
-cudaError_t launch_bwd_prep(const Plan& p, const float* g_log_qz, const float* g_log_qz_prod, const float* g_loss, const float* g_kl,
-                            float beta, const float* S, float* gps, float* gj, float* gk, float* zero, size_t zero_n, cudaStream_t st);
+// Upstream gradients of the backward prologue.  Per row i (any pointer may be null):
+//   gl_i = g_loss[i] + g_loss_mean[0]/b_loc + g_expelbo[0] * (-2*scale/b_loc) * e_rows[i]      (dLoss/dloss_rows[i])
+//   gJ_i = g_log_qz[i] + (beta-1)*gl_i,  gP_i = g_log_qz_prod[i] - (beta-1)*gl_i,  gk_i = gl_i + g_kl[i] + g_kl_mean[0]/b_loc
+// The prologue writes gps = gP/S, gj = gJ, gk (if gk != null), g_rec_rows[i] = the exp-ELBO part of gl_i (the gradient of
+// rec_rows, if asked for) and zeroes `zero_n` floats at `zero` (the column accumulator).
+struct BwdUpstream {
+    const float* g_log_qz; const float* g_log_qz_prod; const float* g_loss; const float* g_kl;
+    const float* g_loss_mean; const float* g_kl_mean; const float* g_expelbo; const float* e_rows; float scale;
+    float* g_rec_rows;
+    float beta;
+};
+cudaError_t launch_bwd_prep(const Plan& p, const BwdUpstream& u, const float* S, float* gps, float* gj, float* gk,
+                            float* zero, size_t zero_n, cudaStream_t st);
 cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* fin, cudaStream_t st);   // fills fin's segment fields
 void set_bwd_variant(int v);          // tools/tune_bwd.py: tuning points of the fused sweep (tc_bwd_ds.cu)
 void set_bwd_seg_target(int v);       // tools/tune_bwd.py: column tiles per CTA segment (0 = default)

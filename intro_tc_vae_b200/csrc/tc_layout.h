@@ -11,6 +11,7 @@ constexpr int kStages     = 3;        // bulk-copy pipeline depth
 constexpr int kRowPad     = 128;      // b_loc / b_glob are padded to a multiple of this
 constexpr int kFwdWarps   = 4;
 constexpr int kBwdWarps   = 8;
+constexpr int kFinWarps   = 8;        // rows (one warp each) per CTA of the forward finalize kernel
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -56,6 +57,7 @@ struct Plan {
     // workspace (byte offsets)
     size_t off_mu, off_zs, off_ns, off_qmax, off_shift, off_vr;   // [bg_pad|bl_pad][dp]
     size_t off_S, off_J2;                                         // persistent forward results
+    size_t off_red; int n_fin_ctas;                               // per-CTA partials + ticket of the finalize kernel's batch means
     size_t off_s2; int64_t ld_s2;                                 // joint exponents [bl_pad][bg_pad]
     size_t off_scratch;                                           // forward split partials (S, J)
     size_t total_bytes;                                           // forward workspace (read-only in backward)
@@ -142,6 +144,8 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.off_vr = off;    off = align256(off + row_arr);
     p.off_S = off;     off = align256(off + row_arr);
     p.off_J2 = off;    off = align256(off + (size_t)p.bl_pad * sizeof(float));
+    p.n_fin_ctas = (b_loc + kFinWarps - 1) / kFinWarps;
+    p.off_red = off;   off = align256(off + ((size_t)3 * p.n_fin_ctas + 4) * sizeof(float));
     p.ld_s2 = p.bg_pad;
     p.off_s2 = off;    off = align256(off + (p.save ? (size_t)p.bl_pad * p.ld_s2 * sizeof(float) : 0));
     const int n_part = p.n_js_fwd > p.slots_fwd ? p.n_js_fwd : p.slots_fwd;

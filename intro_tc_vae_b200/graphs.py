@@ -28,8 +28,8 @@ class GraphedKLLoss:
     ``exchange``: how the column operand and its gradient cross ranks -- ``"nccl"`` (all-gather / reduce-scatter,
     captured in the graph), ``"peer"`` (the library's own kernels over NVLink peer memory,
     :mod:`intro_tc_vae_b200.peer`), or ``"auto"`` (peer memory when it can be set up, NCCL otherwise).
-    ``mode``: ``"direct"`` drives the C ABI itself (reparameterize -> fused loss forward -> fused loss backward ->
-    reparameterize backward, 10 launches); ``"autograd"`` records the same step through ``torch.autograd`` (the
+    ``mode``: ``"direct"`` drives the C ABI itself (tcelbo_klloss_forward_ex / _backward_ex with the reparameterize and
+    batch-mean fusions: 6 launches for the whole step); ``"autograd"`` records the same step through ``torch.autograd`` (the
     public ops plus autograd's fill / accumulate kernels) and exists to cross-check the direct path.
     ``capture=False`` issues the same launches eagerly on every call instead of replaying a graph (for profilers that
     want to see individual launches).
@@ -134,7 +134,9 @@ class GraphedKLLoss:
         self._scratch = None if self.exchange is not None else torch.empty(sc_bytes, dtype=torch.uint8, device=dev)
         self._sc_bytes = sc_bytes
         self._rows = [torch.empty(b_loc, **f32) for _ in range(4)]        # loss, kl, log_qz, log_qz_prod
-        self._g_loss = torch.full((b_loc,), 1.0 / b_loc, **f32)           # d mean / d loss_i
+        self._g_loss = torch.full((b_loc,), 1.0 / b_loc, **f32)           # d mean / d loss_i (peer path: per-row upstream gradient)
+        self._loss = torch.zeros((), **f32)                               # batch mean, written by the forward finalize kernel
+        self._one = torch.ones((), **f32)                                 # dLoss / dloss_mean
         self._gz = torch.empty(b_loc, d, **f32)
         self.dmu = torch.empty(b_loc, d, **f32)
         self.dlogvar = torch.empty(b_loc, d, **f32)
@@ -151,43 +153,48 @@ class GraphedKLLoss:
         P = lambda t: t.data_ptr()                                       # noqa: E731
         rows = [P(t) for t in self._rows]
         exch = self.exchange
+        import ctypes
         with torch.cuda.device(self.device), torch.no_grad():
             st = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(lib.tcelbo_reparam_forward(P(mu), d, P(lv), d, P(eps), d, b_loc, d, P(z), d, st), "tcelbo_reparam_forward")
-            if exch is not None:
-                k = exch.next_forward()
-                exch.mu_sym[k].copy_(mu)
-                exch.mu_hdl.barrier(channel=0)
-                _lib.check(lib.tcelbo_klloss_forward_peer(P(z), d, P(mu), d, P(exch.mu_tables[k]), d, P(lv), d, b_loc, self.world,
-                                                          self.rank, d, n, flags, beta, *rows, P(self._ws), self._ws.numel(), st),
-                           "tcelbo_klloss_forward_peer")
-            else:
+            if exch is None:
+                # 6 launches: prologue (reparameterize + row constants + column padding), forward sweep, finalize (+ batch mean),
+                # backward prologue, fused backward sweep, finalize (+ the chain rule through z = mu + eps * std)
                 mu_all, row_offset = mu, 0
                 if self._mu_all is not None:
                     dist.all_gather_into_tensor(self._mu_all, mu, group=group)
                     mu_all, row_offset = self._mu_all, self.rank * b_loc
-                _lib.check(lib.tcelbo_klloss_forward(P(z), d, P(mu_all), d, P(lv), d, b_loc, mu_all.shape[0], row_offset, d, n, flags,
-                                                     beta, *rows, P(self._ws), self._ws.numel(), st), "tcelbo_klloss_forward")
-            loss = self._rows[0].mean()
-            if exch is not None:
-                k = exch.next_backward()
-                scratch = exch.scratch_sym[k]
-                for phase in (_lib.PEER_SWEEP, _lib.PEER_FINISH):
-                    _lib.check(lib.tcelbo_klloss_backward_peer(phase, P(z), d, P(mu), d, P(lv), d, b_loc, self.world, self.rank, d, n,
-                                                               flags, beta, P(self._g_loss), None, None, None,
-                                                               P(self._gz), d, P(self.dmu), d, P(self.dlogvar), d,
-                                                               P(self._ws), self._ws.numel(), P(scratch), exch.scratch_bytes,
-                                                               P(exch.scratch_tables[k]), st), "tcelbo_klloss_backward_peer")
-                    if phase == _lib.PEER_SWEEP:
-                        exch.scratch_hdl.barrier(channel=0)
-            else:
+                fz = _lib.Fusion(eps=P(eps), ldeps=d, z_out=P(z), ldz_out=d, loss_mean=P(self._loss))
+                _lib.check(lib.tcelbo_klloss_forward_ex(None, 0, P(mu_all), d, P(lv), d, b_loc, mu_all.shape[0], row_offset, d, n, flags,
+                                                        beta, *rows, ctypes.byref(fz), P(self._ws), self._ws.numel(), st),
+                           "tcelbo_klloss_forward_ex")
                 gmu = self._gmu_all if self._gmu_all is not None else self.dmu
-                _lib.check(lib.tcelbo_klloss_backward(P(z), d, P(mu_all), d, P(lv), d, b_loc, mu_all.shape[0], row_offset, d, n, flags,
-                                                      beta, P(self._g_loss), None, None, None, P(self._gz), d, P(gmu), d,
-                                                      P(self.dlogvar), d, P(self._ws), self._ws.numel(),
-                                                      P(self._scratch), self._sc_bytes, st), "tcelbo_klloss_backward")
+                fb = _lib.Fusion(eps=P(eps), ldeps=d, g_loss_mean=P(self._one))
+                _lib.check(lib.tcelbo_klloss_backward_ex(None, 0, P(mu_all), d, P(lv), d, b_loc, mu_all.shape[0], row_offset, d, n, flags,
+                                                         beta, None, None, None, None, ctypes.byref(fb), P(self._gz), d, P(gmu), d,
+                                                         P(self.dlogvar), d, P(self._ws), self._ws.numel(),
+                                                         P(self._scratch), self._sc_bytes, st), "tcelbo_klloss_backward_ex")
                 if self._gmu_all is not None:
                     dist.reduce_scatter_tensor(self.dmu, self._gmu_all, op=dist.ReduceOp.SUM, group=group)
+                return self._loss
+            # peer-memory exchange: the library's prep / finalize kernels gather mu and reduce-scatter its gradient over NVLink
+            _lib.check(lib.tcelbo_reparam_forward(P(mu), d, P(lv), d, P(eps), d, b_loc, d, P(z), d, st), "tcelbo_reparam_forward")
+            k = exch.next_forward()
+            exch.mu_sym[k].copy_(mu)
+            exch.mu_hdl.barrier(channel=0)
+            _lib.check(lib.tcelbo_klloss_forward_peer(P(z), d, P(mu), d, P(exch.mu_tables[k]), d, P(lv), d, b_loc, self.world,
+                                                      self.rank, d, n, flags, beta, *rows, P(self._ws), self._ws.numel(), st),
+                       "tcelbo_klloss_forward_peer")
+            loss = self._rows[0].mean()
+            k = exch.next_backward()
+            scratch = exch.scratch_sym[k]
+            for phase in (_lib.PEER_SWEEP, _lib.PEER_FINISH):
+                _lib.check(lib.tcelbo_klloss_backward_peer(phase, P(z), d, P(mu), d, P(lv), d, b_loc, self.world, self.rank, d, n,
+                                                           flags, beta, P(self._g_loss), None, None, None,
+                                                           P(self._gz), d, P(self.dmu), d, P(self.dlogvar), d,
+                                                           P(self._ws), self._ws.numel(), P(scratch), exch.scratch_bytes,
+                                                           P(exch.scratch_tables[k]), st), "tcelbo_klloss_backward_peer")
+                if phase == _lib.PEER_SWEEP:
+                    exch.scratch_hdl.barrier(channel=0)
             _lib.check(lib.tcelbo_reparam_backward_acc(P(lv), d, P(eps), d, P(self._gz), d, b_loc, d, P(self.dmu), d,
                                                        P(self.dlogvar), d, st), "tcelbo_reparam_backward_acc")
         return loss

@@ -14,6 +14,7 @@ Reference map (file:line in the reference repository):
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Optional, Tuple
 
@@ -161,7 +162,9 @@ _tc_forward.register_autograd(_tc_autograd_backward, setup_context=_tc_setup_con
 # --------------------------------------------------------------------------------------------------
 @torch.library.custom_op("tcelbo::klloss_forward", mutates_args=(), device_types="cuda")
 def _klloss_forward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, dataset_size: int, flags: int,
-                    beta: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+                    beta: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> (loss [B], kl [B], log_qz [B], log_qz_prod [B], loss_mean [], kl_mean [], workspace): the per-sample loss of
+    solvers/tc.py:83-89 and its batch means, the latter reduced inside the finalize kernel (fixed summation order)."""
     lib = _lib.load()
     z, mu_all, logvar = _rows(z), _rows(mu_all), _rows(logvar)
     b_loc, d = z.shape
@@ -171,89 +174,84 @@ def _klloss_forward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, 
         raise NotImplementedError(f"tcelbo: unsupported shape b_loc={b_loc} b_glob={b_glob} d={d} (d must be <= 512)")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
     out = [torch.empty(b_loc, dtype=torch.float32, device=z.device) for _ in range(4)]   # loss, kl, log_qz, log_qz_prod
+    means = [torch.empty((), dtype=torch.float32, device=z.device) for _ in range(2)]
+    fz = _lib.Fusion(loss_mean=means[0].data_ptr(), kl_mean=means[1].data_ptr())
     with torch.cuda.device(z.device):
-        st = lib.tcelbo_klloss_forward(z.data_ptr(), z.stride(0), mu_all.data_ptr(), mu_all.stride(0),
-                                       logvar.data_ptr(), logvar.stride(0), b_loc, b_glob, row_offset, d, dataset_size,
-                                       flags, beta, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
-                                       out[3].data_ptr(), ws.data_ptr(), nbytes, _stream(z))
-    _lib.check(st, "tcelbo_klloss_forward")
-    return out[0], out[1], out[2], out[3], ws
+        st = lib.tcelbo_klloss_forward_ex(z.data_ptr(), z.stride(0), mu_all.data_ptr(), mu_all.stride(0),
+                                          logvar.data_ptr(), logvar.stride(0), b_loc, b_glob, row_offset, d, dataset_size,
+                                          flags, beta, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                          out[3].data_ptr(), ctypes.byref(fz), ws.data_ptr(), nbytes, _stream(z))
+    _lib.check(st, "tcelbo_klloss_forward_ex")
+    return out[0], out[1], out[2], out[3], means[0], means[1], ws
 
 
 @_klloss_forward.register_fake
 def _(z, mu_all, logvar, row_offset, dataset_size, flags, beta):
     nbytes = _lib.load().tcelbo_workspace_bytes(z.shape[0], mu_all.shape[0], z.shape[1], flags)
     b = z.shape[0]
-    return (z.new_empty(b), z.new_empty(b), z.new_empty(b), z.new_empty(b), z.new_empty(nbytes, dtype=torch.uint8))
+    return (z.new_empty(b), z.new_empty(b), z.new_empty(b), z.new_empty(b), z.new_empty(()), z.new_empty(()),
+            z.new_empty(nbytes, dtype=torch.uint8))
 
 
 @torch.library.custom_op("tcelbo::klloss_backward", mutates_args=(), device_types="cuda")
 def _klloss_backward(z: Tensor, mu_all: Tensor, logvar: Tensor, row_offset: int, dataset_size: int, flags: int, beta: float,
-                     g_loss: Tensor, g_kl: Optional[Tensor], g_log_qz: Optional[Tensor], g_log_qz_prod: Optional[Tensor],
+                     g_loss: Optional[Tensor], g_kl: Optional[Tensor], g_log_qz: Optional[Tensor], g_log_qz_prod: Optional[Tensor],
+                     g_loss_mean: Optional[Tensor], g_kl_mean: Optional[Tensor],
                      workspace: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     _alert_not_deterministic("tcelbo::klloss_backward")
     lib = _lib.load()
     z, mu_all, logvar = _rows(z), _rows(mu_all), _rows(logvar)
     b_loc, d = z.shape
     b_glob = mu_all.shape[0]
-    g_loss = g_loss.contiguous()
-    opt = [t.contiguous() if t is not None else None for t in (g_kl, g_log_qz, g_log_qz_prod)]
+    rows = [t.contiguous() if t is not None else None for t in (g_loss, g_kl, g_log_qz, g_log_qz_prod)]
+    scal = [t.contiguous() if t is not None else None for t in (g_loss_mean, g_kl_mean)]
     grad_z = torch.empty(b_loc, d, dtype=torch.float32, device=z.device)
     grad_mu = torch.empty(b_glob, d, dtype=torch.float32, device=z.device)
     grad_lv = torch.empty(b_loc, d, dtype=torch.float32, device=z.device)
     nscratch = lib.tcelbo_backward_scratch_bytes(b_loc, b_glob, d, flags)
     scratch = torch.empty(nscratch, dtype=torch.uint8, device=z.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None                      # noqa: E731
+    fz = _lib.Fusion(g_loss_mean=ptr(scal[0]), g_kl_mean=ptr(scal[1]))
     with torch.cuda.device(z.device):
-        st = lib.tcelbo_klloss_backward(z.data_ptr(), z.stride(0), mu_all.data_ptr(), mu_all.stride(0),
-                                        logvar.data_ptr(), logvar.stride(0), b_loc, b_glob, row_offset, d, dataset_size,
-                                        flags, beta, g_loss.data_ptr(), *(t.data_ptr() if t is not None else None for t in opt),
-                                        grad_z.data_ptr(), d, grad_mu.data_ptr(), d, grad_lv.data_ptr(), d,
-                                        workspace.data_ptr(), workspace.numel(), scratch.data_ptr(), nscratch, _stream(z))
-    _lib.check(st, "tcelbo_klloss_backward")
+        st = lib.tcelbo_klloss_backward_ex(z.data_ptr(), z.stride(0), mu_all.data_ptr(), mu_all.stride(0),
+                                           logvar.data_ptr(), logvar.stride(0), b_loc, b_glob, row_offset, d, dataset_size,
+                                           flags, beta, *(ptr(t) for t in rows), ctypes.byref(fz),
+                                           grad_z.data_ptr(), d, grad_mu.data_ptr(), d, grad_lv.data_ptr(), d,
+                                           workspace.data_ptr(), workspace.numel(), scratch.data_ptr(), nscratch, _stream(z))
+    _lib.check(st, "tcelbo_klloss_backward_ex")
     return grad_z, grad_mu, grad_lv
 
 
 @_klloss_backward.register_fake
-def _(z, mu_all, logvar, row_offset, dataset_size, flags, beta, g_loss, g_kl, g_log_qz, g_log_qz_prod, workspace):
+def _(z, mu_all, logvar, row_offset, dataset_size, flags, beta, g_loss, g_kl, g_log_qz, g_log_qz_prod, g_loss_mean, g_kl_mean,
+      workspace):
     return (z.new_empty(z.shape), mu_all.new_empty(mu_all.shape), logvar.new_empty(logvar.shape))
 
 
 def _klloss_setup_context(ctx, inputs, output):
     ctx.set_materialize_grads(False)          # unused outputs arrive as None instead of zero-filled tensors
     z, mu_all, logvar, row_offset, dataset_size, flags, beta = inputs
-    ctx.save_for_backward(z, mu_all, logvar, output[4])
+    ctx.save_for_backward(z, mu_all, logvar, output[6])
     ctx.meta = (row_offset, dataset_size, flags, beta)
 
 
-def _klloss_autograd_backward(ctx, g_loss, g_kl, g_log_qz, g_log_qz_prod, _g_ws):
+def _klloss_autograd_backward(ctx, g_loss, g_kl, g_log_qz, g_log_qz_prod, g_loss_mean, g_kl_mean, _g_ws):
     z, mu_all, logvar, ws = ctx.saved_tensors
     row_offset, dataset_size, flags, beta = ctx.meta
     if not flags & _lib.SAVE_FOR_BACKWARD:
         raise RuntimeError("tcelbo: forward ran without TCELBO_SAVE_FOR_BACKWARD but a gradient was requested")
-    if g_loss is None and g_kl is None and g_log_qz is None and g_log_qz_prod is None:
+    if all(g is None for g in (g_loss, g_kl, g_log_qz, g_log_qz_prod, g_loss_mean, g_kl_mean)):
         return None, None, None, None, None, None, None
-    if g_loss is None:
-        g_loss = torch.zeros(z.shape[0], dtype=torch.float32, device=z.device)
     gz, gmu, glv = _klloss_backward(z, mu_all, logvar, row_offset, dataset_size, flags, beta,
-                                    g_loss, g_kl, g_log_qz, g_log_qz_prod, ws)
+                                    g_loss, g_kl, g_log_qz, g_log_qz_prod, g_loss_mean, g_kl_mean, ws)
     return gz, gmu, glv, None, None, None, None
 
 
 _klloss_forward.register_autograd(_klloss_autograd_backward, setup_context=_klloss_setup_context)
 
 
-def kl_tc_loss_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, beta: float, estimator: str = "mss",
-                     group=None, exchange=None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """One fused evaluation of ``TCSovler._compute_kl_loss_simple`` (solvers/tc.py:69-89) per sample:
-
-        loss_i = (beta - 1) * (log_qz_i - log_qz_prod_i) + kl_i ,   kl_i = ops.py:161-163
-
-    Returns ``(loss [B], kl [B], log_qz [B], log_qz_prod [B])``.  KL and the combine are folded into the TC
-    kernels' finalize steps (forward and backward), so no separate KL or elementwise kernels are launched.
-    ``group`` row-shards the batch exactly as in :func:`tc_terms` (NCCL all-gather / reduce-scatter around the kernels);
-    ``exchange`` (a :class:`intro_tc_vae_b200.peer.PeerExchange`) row-shards it over the exchange's group with both
-    exchange steps done by the library's kernels over NVLink peer memory instead.
-    """
+def _klloss(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, beta: float, estimator: str, group, exchange):
+    """Shared front end of :func:`kl_tc_loss_terms` / :func:`kl_tc_loss_mean` -> the op's 6 tensor outputs."""
     for name, t in (("z", z), ("mu", mu), ("logvar", logvar)):
         _check(name, t)
     if not (z.shape == mu.shape == logvar.shape):
@@ -268,7 +266,8 @@ def kl_tc_loss_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, b
         from .peer import kl_tc_loss_terms_peer
         if estimator == "mss" and exchange.world * z.shape[0] == 1:
             raise ZeroDivisionError("float division by zero")
-        return kl_tc_loss_terms_peer(z, mu, logvar, dataset_size, beta, flags, exchange)
+        loss, kl, log_qz, log_qz_prod = kl_tc_loss_terms_peer(z, mu, logvar, dataset_size, beta, flags, exchange)
+        return loss, kl, log_qz, log_qz_prod, None, None
     if group is not None:
         import torch.distributed as dist
         if dist.get_world_size(group) > 1:
@@ -276,16 +275,34 @@ def kl_tc_loss_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, b
             mu_all = gather_rows(mu, group)
     if estimator == "mss" and mu_all.shape[0] == 1:
         raise ZeroDivisionError("float division by zero")       # ops.py:44 with M = B-1 = 0
-    loss, kl, log_qz, log_qz_prod, _ = _klloss_forward(z, mu_all, logvar, row_offset, int(dataset_size), flags, float(beta))
-    return loss, kl, log_qz, log_qz_prod
+    return _klloss_forward(z, mu_all, logvar, row_offset, int(dataset_size), flags, float(beta))[:6]
+
+
+def kl_tc_loss_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, beta: float, estimator: str = "mss",
+                     group=None, exchange=None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """One fused evaluation of ``TCSovler._compute_kl_loss_simple`` (solvers/tc.py:69-89) per sample:
+
+        loss_i = (beta - 1) * (log_qz_i - log_qz_prod_i) + kl_i ,   kl_i = ops.py:161-163
+
+    Returns ``(loss [B], kl [B], log_qz [B], log_qz_prod [B])``.  KL and the combine are folded into the TC
+    kernels' finalize steps (forward and backward), so no separate KL or elementwise kernels are launched.
+    ``group`` row-shards the batch exactly as in :func:`tc_terms` (NCCL all-gather / reduce-scatter around the kernels);
+    ``exchange`` (a :class:`intro_tc_vae_b200.peer.PeerExchange`) row-shards it over the exchange's group with both
+    exchange steps done by the library's kernels over NVLink peer memory instead.
+    """
+    return _klloss(z, mu, logvar, dataset_size, beta, estimator, group, exchange)[:4]
 
 
 def kl_tc_loss_mean(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, beta: float, estimator: str = "mss",
                     group=None, exchange=None) -> Tuple[Tensor, Tensor]:
     """``reduce="mean"`` form of :func:`kl_tc_loss_terms`: 0-d ``(mean_i[(beta-1)*tc_i + kl_i], mean_i kl_i)``
-    (solvers/tc.py:83-89 with the default reduce).  Row-sharded calls return the mean over the local rows."""
-    loss, kl, _, _ = kl_tc_loss_terms(z, mu, logvar, dataset_size, beta, estimator, group, exchange)
-    return loss.mean(), kl.mean()
+    (solvers/tc.py:83-89 with the default reduce).  The means come out of the finalize kernel itself (deterministic
+    last-CTA reduction) and their gradients enter the backward prologue as device scalars, so no reduction, expand or
+    elementwise kernels surround the op.  Row-sharded calls return the mean over the local rows."""
+    loss, kl, _, _, loss_mean, kl_mean = _klloss(z, mu, logvar, dataset_size, beta, estimator, group, exchange)
+    if loss_mean is None:                                        # peer-memory path: per-row outputs only
+        return loss.mean(), kl.mean()
+    return loss_mean, kl_mean
 
 
 def tc_terms(z: Tensor, mu: Tensor, logvar: Tensor, dataset_size: int, estimator: str = "mss",

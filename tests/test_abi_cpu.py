@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/tcelbo.h but not exported by libtcelbo.so"
     assert set(declared) == set(_lib.EXPORTED_SYMBOLS)
-    assert lib.tcelbo_version() == 1
+    assert lib.tcelbo_version() == 2
 
 
 def test_workspace_planner_without_gpu():

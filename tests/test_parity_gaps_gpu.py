@@ -285,3 +285,79 @@ def test_non_finite_inputs_propagate_like_the_reference(B, D, what):
     record("non_finite", f"{what}_B{B}_D{D}", loss=_finite_relerr(loss, loss_o), dmu=_finite_relerr(mu.grad, mu_o.grad),
            dlv=_finite_relerr(lv.grad, lv_o.grad), extra_nan_dmu=float((torch.isnan(mu.grad).cpu() & ~torch.isnan(mu_o.grad)).sum()),
            extra_nan_dlv=float((torch.isnan(lv.grad).cpu() & ~torch.isnan(lv_o.grad)).sum()))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused prologue / epilogue of the loss op
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,D,family", [(64, 128, "base"), (200, 20, "sharp"), (130, 256, "base")])
+def test_fused_reparameterize_and_batch_mean_against_oracle(B, D, family):
+    """tcelbo_klloss_forward_ex / _backward_ex with eps (reparameterize in the prologue, chain rule through z in the backward
+    finalize) and loss_mean (reduced in the forward finalize) == the oracle's reparameterize -> compute_kl_loss(mean) -> backward,
+    i.e. ops.py:183-185 + solvers/tc.py:69-89.  GraphedKLLoss's direct step is exactly this call sequence (6 launches)."""
+    from intro_tc_vae_b200 import _lib
+    from intro_tc_vae_b200.graphs import GraphedKLLoss
+    N, beta = 16704, 0.5
+    mu_c, lv_c, eps_c = _latents(B, D, family, seed=23)
+    mu_o, lv_o = mu_c.clone().requires_grad_(True), lv_c.clone().requires_grad_(True)
+    z_o = O.reparameterize(mu_o, lv_o, eps_c)
+    loss_o = O.kl_loss_simple(z_o, mu_o, lv_o, N, beta, "mean")
+    loss_o.backward()
+    lib = _lib.load()
+    graphed = GraphedKLLoss(B, D, N, beta, "cuda:0", capture=False)
+    c0 = lib.tcelbo_launch_count()
+    loss, dmu, dlv = graphed(mu_c.cuda(), lv_c.cuda(), eps_c.cuda())
+    torch.cuda.synchronize()
+    assert lib.tcelbo_launch_count() - c0 == 6
+    errs = dict(loss=abs(loss.item() - loss_o.item()) / abs(loss_o.item()), z=relerr(graphed._z, z_o),
+                dmu=relerr(dmu, mu_o.grad), dlv=relerr(dlv, lv_o.grad))
+    record("fused_reparam_mean", f"{family}_B{B}_D{D}", **errs)
+    assert errs["loss"] < LOSS_RTOL and errs["z"] < 1e-6 and errs["dmu"] < GRAD_RTOL and errs["dlv"] < GRAD_RTOL
+
+
+@pytest.mark.parametrize("B,D,family", [(64, 128, "base"), (96, 32, "sharp")])
+def test_mean_reduced_op_equals_reference_mean(B, D, family):
+    """ops.kl_tc_loss_mean (what compute_kl_loss(reduce="mean") calls): loss, the KL it logs, and gradients vs the oracle."""
+    ops = _ops()
+    N, beta = 16704, 6.0
+    mu_c, lv_c, eps_c = _latents(B, D, family, seed=29)
+    mu_o, lv_o = mu_c.clone().requires_grad_(True), lv_c.clone().requires_grad_(True)
+    z_o = O.reparameterize(mu_o, lv_o, eps_c)
+    loss_o = O.kl_loss_simple(z_o, mu_o, lv_o, N, beta, "mean")
+    kl_o = O.kl_divergence(lv_o, mu_o, "mean")
+    (loss_o + 0.25 * kl_o).backward()
+    mu, lv = mu_c.cuda().requires_grad_(True), lv_c.cuda().requires_grad_(True)
+    z = ops.reparameterize(mu, lv, eps_c.cuda())
+    loss, kl = ops.kl_tc_loss_mean(z, mu, lv, N, beta)
+    assert loss.dim() == 0 and kl.dim() == 0
+    (loss + 0.25 * kl).backward()
+    errs = dict(loss=abs(loss.item() - loss_o.item()) / abs(loss_o.item()), kl=abs(kl.item() - kl_o.item()) / abs(kl_o.item()),
+                dmu=relerr(mu.grad, mu_o.grad), dlv=relerr(lv.grad, lv_o.grad))
+    record("mean_op", f"{family}_B{B}_D{D}", **errs)
+    assert errs["loss"] < LOSS_RTOL and errs["kl"] < LOSS_RTOL and errs["dmu"] < GRAD_RTOL and errs["dlv"] < GRAD_RTOL
+
+
+@pytest.mark.parametrize("B,D,family,beta", [(64, 128, "base", 512.0), (150, 32, "sharp", 256.0)])
+def test_fused_exp_elbo_against_reference_formula(B, D, family, beta):
+    """solvers/intro.py:84-89,102-103: exp(-2*scale*(rec_i + kl_i)).mean() with kl_i from compute_kl_loss(reduce="none",
+    beta=beta_neg), fused into the loss op's finalize / backward prologue, vs the oracle's composition; gradients to mu, logvar
+    (through z) and to the per-sample reconstruction loss."""
+    from intro_tc_vae_b200.losses import kl_tc_exp_elbo
+    ops = _ops()
+    N, scale = 16704, 1.0 / (3 * 64 * 64)
+    mu_c, lv_c, eps_c = _latents(B, D, family, seed=31)
+    rec_c = 40.0 + 25.0 * torch.rand(B, generator=torch.Generator().manual_seed(4))
+    mu_o, lv_o, rec_o = mu_c.clone().requires_grad_(True), lv_c.clone().requires_grad_(True), rec_c.clone().requires_grad_(True)
+    z_o = O.reparameterize(mu_o, lv_o, eps_c)
+    kl_rows_o = O.kl_loss_simple(z_o, mu_o, lv_o, N, beta, "none")
+    ee_o = O.exp_elbo(rec_o, kl_rows_o, scale)
+    ee_o.backward()
+    mu, lv, rec = mu_c.cuda().requires_grad_(True), lv_c.cuda().requires_grad_(True), rec_c.cuda().requires_grad_(True)
+    z = ops.reparameterize(mu, lv, eps_c.cuda())
+    ee, kl_rows = kl_tc_exp_elbo(z, mu, lv, rec, N, beta, scale)
+    ee.backward()
+    errs = dict(expelbo=abs(ee.item() - ee_o.item()) / abs(ee_o.item()), kl_rows=relerr(kl_rows, kl_rows_o),
+                dmu=relerr(mu.grad, mu_o.grad), dlv=relerr(lv.grad, lv_o.grad), drec=relerr(rec.grad, rec_o.grad))
+    record("fused_exp_elbo", f"{family}_B{B}_D{D}", **errs)
+    assert errs["expelbo"] < LOSS_RTOL and errs["kl_rows"] < LOSS_RTOL
+    assert errs["dmu"] < GRAD_RTOL and errs["dlv"] < GRAD_RTOL and errs["drec"] < GRAD_RTOL

@@ -1,11 +1,11 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python tools/tune_bwd.py --variants=0,1,2,3,4,5,6,7,8,9,10,11,12 --reps 5 > gpurun_out/r2e_tune_8192.log 2>&1
-timeout 300 python tools/tune_bwd.py --variants=0,4,6,9 --reps 7 --rows 1024 > gpurun_out/r2e_tune_1024.log 2>&1
-timeout 300 python tools/tune_bwd.py --variants=0,4 --reps 5 --batch 4096 --zdim 512 > gpurun_out/r2e_tune_d512.log 2>&1
-timeout 300 python tools/tune_bwd.py --variants=0 --reps 5 --batch 4096 --zdim 64 > gpurun_out/r2e_tune_d64.log 2>&1
-timeout 300 python tools/tune_bwd.py --variants=0 --reps 5 --batch 4000 --zdim 20 > gpurun_out/r2e_tune_d20.log 2>&1
-cat gpurun_out/r2e_tune_*.log
-timeout 2400 python -m pytest tests -m gpu -q --timeout=1500 -k "cfg4 or peer or non_finite or seeded or golden" > gpurun_out/r2e_pytest.log 2>&1
-tail -5 gpurun_out/r2e_pytest.log
+timeout 2400 python -m pytest tests -m gpu -q --timeout=1500 -x > gpurun_out/r2f_pytest.log 2>&1
+tail -15 gpurun_out/r2f_pytest.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err
+tail -3 gpurun_out/r2f_bench.err
+python -c "
+import json;j=json.load(open('gpurun_out/r2f_bench.json'))
+print({k:j[k] for k in ('ms_per_step','value','gpu_launches')}, j['e2e'], j['dropin'], j['e2e_dropin'], j['roofline']['kernel_ms'], j['roofline']['step_frac_of_sfu_peak'], j['cpu_baseline'])
+"
