@@ -452,6 +452,11 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
 
 // variant 0 is the shipped configuration; the others are tuning points kept for tools/tune_bwd.py (profiles/r2_bwd_ds_sweep.md)
 static cudaError_t launch_bwd_ds(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* fin, int variant, cudaStream_t st) {
+    if (p.small) {                       // B = 3 / 64-sized batches: 4 rows per warp so that row blocks x tiles covers more SMs
+        if (p.dp >= 128) return launch_bwd_ds_t<2, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);
+        if (p.dp == 64) return launch_bwd_ds_t<2, 2, 8, 2, 16, 8, false, true>(p, a, fin, st);
+        return launch_bwd_ds_t<2, 1, 8, 2, 16, 8, false, true>(p, a, fin, st);
+    }
     if (p.dp >= 128) {
         switch (variant) {
             case 1:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 8>(p, a, fin, st);               // 12 rows/warp, 16 warps/SM, mask by multiply

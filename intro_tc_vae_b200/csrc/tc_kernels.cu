@@ -144,13 +144,13 @@ __device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt,
     }
 }
 
-template <int LPR>
+template <int LPR, int JTS>     // JTS: columns per tile (0 = as many as fit kTileFloats, at most 32)
 __global__ void __launch_bounds__(kFwdWarps * 32, 3)
 tc_fwd_kernel(const FwdArgs a) {
     constexpr int DP = 32 * LPR;
     constexpr int RPW = 32 / LPR;
     constexpr int ROWS = kFwdWarps * RPW;
-    constexpr int JT = (kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP);
+    constexpr int JT = JTS > 0 ? JTS : ((kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP));
     constexpr int TILE = JT * DP;
     constexpr int G = LPR < 4 ? LPR : 4;
 
@@ -421,20 +421,20 @@ static inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
     return (int)g;
 }
 
-template <int LPR>
+template <int LPR, int JTS>
 static cudaError_t launch_fwd_t(const Plan& p, const FwdArgs& a, cudaStream_t st) {
     constexpr int DP = 32 * LPR;
-    constexpr int JT = (kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP);
+    constexpr int JT = JTS > 0 ? JTS : ((kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP));
     const size_t smem = (size_t)kStages * JT * DP * sizeof(float) + 2 * kStages * sizeof(uint64_t);
     static PerDevice configured_on;
     int& configured = configured_on.cur();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<LPR, JTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = 1;
     }
     LaunchScope scope(kKernFwd, st);
-    tc_fwd_kernel<LPR><<<p.seg_fwd.n_ctas, kFwdWarps * 32, smem, st>>>(a);
+    tc_fwd_kernel<LPR, JTS><<<p.seg_fwd.n_ctas, kFwdWarps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -447,12 +447,22 @@ cudaError_t launch_prep(const PrepArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st) {
+    if (p.small) {
+        switch (p.dpt) {
+            case 1:  return launch_fwd_t<1, kSmallTile>(p, a, st);
+            case 2:  return launch_fwd_t<2, kSmallTile>(p, a, st);
+            case 4:  return launch_fwd_t<4, kSmallTile>(p, a, st);
+            case 8:  return launch_fwd_t<8, kSmallTile>(p, a, st);
+            case 16: return launch_fwd_t<16, kSmallTile>(p, a, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (p.dpt) {
-        case 1:  return launch_fwd_t<1>(p, a, st);
-        case 2:  return launch_fwd_t<2>(p, a, st);
-        case 4:  return launch_fwd_t<4>(p, a, st);
-        case 8:  return launch_fwd_t<8>(p, a, st);
-        case 16: return launch_fwd_t<16>(p, a, st);
+        case 1:  return launch_fwd_t<1, 0>(p, a, st);
+        case 2:  return launch_fwd_t<2, 0>(p, a, st);
+        case 4:  return launch_fwd_t<4, 0>(p, a, st);
+        case 8:  return launch_fwd_t<8, 0>(p, a, st);
+        case 16: return launch_fwd_t<16, 0>(p, a, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -8,7 +8,9 @@ namespace tcelbo {
 
 constexpr int kTileFloats = 4096;     // floats of column data per pipeline stage (16 KiB)
 constexpr int kStages     = 3;        // bulk-copy pipeline depth
-constexpr int kRowPad     = 128;      // b_loc / b_glob are padded to a multiple of this
+constexpr int kRowPad     = 128;      // column-variance sweeps: b_loc / b_glob are padded to a multiple of this
+constexpr int kColPad     = 32;       // row-variance sweeps: columns pad to this (one forward tile, two backward tiles)
+constexpr int kSmallTile  = 4;        // forward column tile of the small-problem instantiation
 constexpr int kFwdWarps   = 4;
 constexpr int kBwdWarps   = 8;
 constexpr int kFinWarps   = 8;        // rows (one warp each) per CTA of the forward finalize kernel
@@ -64,6 +66,7 @@ struct Plan {
     // backward scratch (its own buffer, so the forward workspace stays immutable and backward can be re-run)
     size_t boff_gps, boff_gj, boff_gk, boff_A, boff_CR, boff_G, bwd_bytes;
     bool save, var_col;
+    bool small;                // fewer work units than SMs with the standard tiles: small-tile / few-rows instantiations
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -92,7 +95,7 @@ inline void choose_splits(int n_blocks, int slots, int len, int quantum, int min
 inline Segments plan_segments(int64_t n_blocks, int tiles_per_block, int slots, int target_tiles) {
     const int64_t total = n_blocks * tiles_per_block;
     int64_t min_seg = (tiles_per_block - 1 + (kMaxSplits - 3)) / (kMaxSplits - 2);   // (T-1)/base + 2 <= kMaxSplits
-    if (min_seg < 4) min_seg = tiles_per_block < 4 ? tiles_per_block : 4;
+    if (min_seg < 1) min_seg = 1;                 // small problems: down to one tile per CTA, so that they still spread over the SMs
     const int64_t want = target_tiles > min_seg ? target_tiles : min_seg;
     int64_t waves = (total + (int64_t)slots * want / 2) / ((int64_t)slots * want);    // nearest whole number of waves
     if (waves < 1) waves = 1;
@@ -114,16 +117,21 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     int dp = 32; while (dp < d) dp <<= 1;
     p.dp = dp; p.dpt = dp / 32;
     p.b_loc = b_loc; p.b_glob = b_glob;
-    p.bl_pad = (int)round_up(b_loc, kRowPad);
-    p.bg_pad = (int)round_up(b_glob, kRowPad);
-    p.jt = kTileFloats / dp;                                   // 128 .. 8
-    if (p.jt > 32) p.jt = 32;
     p.save = (flags & 4u) != 0;
     p.var_col = (flags & 2u) != 0;
-
-    // ---- forward: a CTA owns fwd_rows rows and a contiguous range of js_len columns
+    // ---- forward: a CTA owns fwd_rows rows and a contiguous range of columns
     p.fwd_rows = kFwdWarps * (32 / p.dpt);
+    // rows pad to whole forward row blocks (32 rows at D >= 128), columns to whole 32-column tiles; the column-variance sweeps
+    // keep the 128-row padding their uniform grids were written for
+    const int row_pad = p.var_col ? kRowPad : (p.fwd_rows > kColPad ? p.fwd_rows : kColPad);
+    p.bl_pad = (int)round_up(b_loc, row_pad);
+    p.bg_pad = (int)round_up(b_glob, p.var_col ? kRowPad : kColPad);
+    p.jt = kTileFloats / dp;                                   // 128 .. 8
+    if (p.jt > 32) p.jt = 32;
     p.n_rb_fwd = p.bl_pad / p.fwd_rows;
+    // small problems (BASELINE cfg 1 / 2: B = 3 / 64): 4-column tiles, so that row blocks x tiles still gives every SM a CTA
+    p.small = !p.var_col && (int64_t)p.n_rb_fwd * (p.bg_pad / p.jt) < sms;
+    if (p.small) p.jt = kSmallTile;
     choose_splits(p.n_rb_fwd, sms * 3, p.bg_pad, p.jt, 4, p.n_js_fwd, p.js_len_fwd);   // 3 resident CTAs per SM
     p.tiles_fwd = p.bg_pad / p.jt;
     p.seg_fwd = plan_segments(p.n_rb_fwd, p.tiles_fwd, sms * 3, fwd_seg_target() > 0 ? fwd_seg_target() : 21);

@@ -100,3 +100,46 @@ def test_installed_compute_kl_loss_equals_reference_on_identical_latents():
         assert rel(rows, ref["rows"]) <= 1e-5
         assert rel(mu.grad, ref["gmu"]) <= 1e-4
         assert rel(lv.grad, ref["glv"]) <= 1e-4
+
+
+@pytest.mark.parametrize("capture", [False, True])
+def test_graphed_soft_intro_step_matches_the_reference_train_step(capture):
+    """intro_tc_vae_b200.train_step.SoftIntroTCStep (no host synchronisation, optionally two CUDA graphs) performs the update of
+    the reference's IntroTCSovler.train_step (solvers/intro.py:56-196): same seeds -> same losses on the first step and the same
+    parameters afterwards (up to Adam's amplification of last-bit gradient differences), on the reference's own SoftIntroVAE."""
+    dev = torch.device("cuda:0")
+    B = 48
+    batch = torch.rand(B, 3, 16, 16, generator=torch.Generator().manual_seed(5))
+    with ref_loader.on_path():
+        model, solver = _build("intro-tc", dev, installed=False)
+        torch.manual_seed(11)
+        torch.cuda.manual_seed(11)
+        noise = torch.randn(B, model.zdim)                      # what solvers/intro.py:61 draws first from the CPU generator
+        torch.manual_seed(11)
+        init_params = [p.detach().clone() for p in model.parameters()]
+        ref_out = solver.train_step(batch, 0)
+        ref_params = [p.detach().clone() for p in model.parameters()]
+    with ref_loader.on_path():
+        import models
+        import intro_tc_vae_b200
+        from intro_tc_vae_b200.train_step import SoftIntroTCStep
+        intro_tc_vae_b200.install()
+        torch.manual_seed(0)
+        model = models.SoftIntroVAE(arch="conv", cdim=3, zdim=32, channels=(16, 32), image_size=16).to(dev)
+        opt_e = torch.optim.Adam(model.encoder.parameters(), lr=2e-4, capturable=True)
+        opt_d = torch.optim.Adam(model.decoder.parameters(), lr=2e-4, capturable=True)
+        step = SoftIntroTCStep(model, opt_e, opt_d, N_DATA, batch.shape, recon_loss_type="mse", beta_kl=0.5, beta_rec=0.75,
+                               beta_neg=512.0, gamma_r=1e-8, clip=100.0, capture=capture)
+        torch.cuda.manual_seed(11)
+        out = step(batch.to(dev), noise.to(dev))
+        step.check_finite()
+        got = {k: v.item() for k, v in out.items()}
+        for key, tol in (("loss_enc", 1e-4), ("loss_kl", 1e-4), ("loss_rec", 1e-4), ("loss_dec", 2e-3)):
+            assert abs(got[key] - ref_out[key]) <= tol * max(abs(ref_out[key]), 1e-3), (capture, key, got[key], ref_out[key])
+        assert abs(max(got["norm_e"], got["norm_d"]) - ref_out["L2"]) <= 1e-3 * ref_out["L2"]
+        # Adam's first update is lr * g / |g| per weight, so weights whose gradient is ~0 may step the other way on last-bit
+        # differences; the two update vectors must still point the same way overall
+        u_ref = torch.cat([(q - p0).flatten() for q, p0 in zip(ref_params, init_params)])
+        u_got = torch.cat([(p.detach() - p0).flatten() for p, p0 in zip(model.parameters(), init_params)])
+        cos = torch.dot(u_ref, u_got) / (u_ref.norm() * u_got.norm())
+        assert cos.item() > 0.99, (capture, cos.item())
