@@ -480,6 +480,24 @@ def run_ours(args):
                "sample": cpu_sample_note(CPU_SAMPLE_B, D, kind, cores) + ", best of 3",
                "fwd_ms": 1e3 * min(f for f, _ in times), "bwd_ms": 1e3 * min(w for _, w in times)}
 
+    # ---- BASELINE.json metric 2: Soft-Intro-TC train images/s on synthetic images (tools/train_bench.py harness around
+    #      intro_tc_vae_b200.train_step.SoftIntroTCStep).  N=1: configs[1] shape (64x64, z 128, batch 64); N>1: configs[4] shape
+    #      (128x128, z 256, batch 32 per GPU, data parallel with the TC estimator row-sharded over the ranks).
+    train = None
+    if not args.no_train:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import train_bench
+            if world == 1:
+                train = train_bench.measure(64, 128, 64, steps=20, warmup=5, dev=dev)
+                train["config"] = "BASELINE configs[1] shape: 64x64x3 synthetic images, conv arch, z_dim 128, batch 64, fp32 (no AMP in the reference)"
+            else:
+                train = train_bench.measure(128, 256, 32, steps=15, warmup=5, dev=dev, group=group, peer=(exchange_note == "peer"))
+                train["config"] = f"BASELINE configs[4] shape: 128x128x3 synthetic images, z_dim 256, beta_neg 512, batch 32 per GPU, data parallel x{world}"
+        except Exception as exc:
+            train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        barrier()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -503,6 +521,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "train_images_per_s": (train or {}).get("value"),
+            "train": train,
             "wall_s_timed_region": t_wall1 - t_wall0,
         }
         print(json.dumps(line), flush=True)
@@ -526,6 +546,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="GLOBAL batch (rows are sharded over the ranks)")
     ap.add_argument("--zdim", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the Soft-Intro-TC train images/s leg")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="N>1: how the column operand / its gradient cross ranks (peer memory inside the kernels, or NCCL)")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a captured CUDA graph")

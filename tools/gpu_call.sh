@@ -1,13 +1,16 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 2400 python -m pytest tests -m gpu -q --timeout=1500 -x > gpurun_out/r2f_pytest.log 2>&1
-tail -15 gpurun_out/r2f_pytest.log
-timeout 300 python tools/small_batch_bench.py --batch 64 > gpurun_out/r2f_small64.json 2> gpurun_out/r2f_small.err; cat gpurun_out/r2f_small64.json; tail -3 gpurun_out/r2f_small.err
-timeout 300 python tools/small_batch_bench.py --batch 3 > gpurun_out/r2f_small3.json 2>> gpurun_out/r2f_small.err; cat gpurun_out/r2f_small3.json
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err
-tail -3 gpurun_out/r2f_bench.err
+for N in 8 4; do
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2h_bench_n$N.json 2> gpurun_out/r2h_bench_n$N.err
+tail -2 gpurun_out/r2h_bench_n$N.err
 python -c "
-import json;j=json.load(open('gpurun_out/r2f_bench.json'))
-print({k:j[k] for k in ('ms_per_step','value','gpu_launches')}, j['e2e'], j['dropin'], j['e2e_dropin'], j['roofline']['kernel_ms'], j['roofline']['step_frac_of_sfu_peak'], j['cpu_baseline'])
+import json;j=json.loads([l for l in open('gpurun_out/r2h_bench_n$N.json') if l.startswith('{')][-1])
+print($N, {k:j[k] for k in ('ms_per_step','value','gpu_launches')}, j['e2e']['ms_per_step'], j['dropin']['ms_per_step'], j['e2e_dropin']['ms_per_step'], j['roofline']['kernel_ms'], j['config']['exchange'], j['train'])
+"
+done
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 8 --steps 20 --warmup 5 --exchange nccl --no-train > gpurun_out/r2h_bench_n8_nccl.json 2> gpurun_out/r2h_bench_n8_nccl.err
+python -c "
+import json;j=json.loads([l for l in open('gpurun_out/r2h_bench_n8_nccl.json') if l.startswith('{')][-1])
+print('nccl', {k:j[k] for k in ('ms_per_step','value')}, j['e2e']['ms_per_step'], j['dropin']['ms_per_step'], j['e2e_dropin']['ms_per_step'], j['config']['exchange'])
 "

@@ -1,12 +1,14 @@
-"""Soft-Intro-TC training-step throughput on synthetic images (BASELINE configs[1] / [4] shapes).
+"""Soft-Intro-TC training-step throughput on synthetic images (BASELINE configs[1] / [4] shapes; BASELINE.json metric 2).
 
-    python tools/train_bench.py [--image 64] [--zdim 128] [--batch 64] [--steps 30] [--warmup 10]
+    python tools/train_bench.py [--image 64] [--zdim 128] [--batch 64] [--steps 30] [--warmup 10] [--eager]
     python -m torch.distributed.run --nproc-per-node N ... tools/train_bench.py   # data parallel, TC estimator row-sharded
 
-The conv encoder/decoder are stock torch modules in the reference's "conv" recipe (models.py:8-55,190-300: 5x5 stem,
-double-3x3 conv blocks with BatchNorm + LeakyReLU, AvgPool down / nearest-neighbour up, fc -> chunked mu/logvar); they
-are NOT part of the accelerated path.  Every loss term (reparameterize, KL + TC, reconstruction, exp-ELBO) runs through
-libtcelbo.so via intro_tc_vae_b200.solvers.IntroTCSovler.  Prints one JSON line (images/s over all ranks).
+Harness only.  The conv encoder/decoder are stock torch modules in the reference's "conv" recipe (models.py:8-55,190-300:
+5x5 stem, double-3x3 conv blocks with BatchNorm + LeakyReLU, AvgPool down / nearest-neighbour up, fc -> chunked mu/logvar);
+they are NOT part of the accelerated path and stand in for the reference's models.SoftIntroVAE, which is not on the GPU box.
+The update itself is intro_tc_vae_b200.train_step.SoftIntroTCStep: the Soft-Intro-TC step of solvers/intro.py:56-196 with every
+loss term (reparameterize, KL + TC, reconstruction, exp-ELBO) on libtcelbo.so, captured in two CUDA graphs, no host
+synchronisation.  Prints one JSON line (images/s over all ranks); bench.py calls measure() for its train_images_per_s keys.
 """
 import argparse
 import json
@@ -18,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.distributed as dist
 from intro_tc_vae_b200 import ops
-from intro_tc_vae_b200.solvers import IntroTCSovler
+from intro_tc_vae_b200.train_step import SoftIntroTCStep
 
 
 def block(cin, cout):
@@ -83,24 +85,45 @@ class ConvVAE(nn.Module):
         return mu, logvar, z, self.decode(z)
 
 
-class _Dataset:
-    def __len__(self):
-        return 16704
-
-
-class DPSolver(IntroTCSovler):
-    """Data-parallel harness: average .grad over the ranks after every backward (one flattened all-reduce)."""
-
-    def sync_gradients(self, params):
-        if self.process_group is None:
-            return
-        grads = [p.grad for p in params if p.grad is not None]
-        if not grads:
-            return
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.process_group)
-        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g.copy_(f)
+def measure(image, zdim, batch, steps, warmup, dev, group=None, peer=False, capture=True):
+    """images/s of the Soft-Intro-TC update on a fixed synthetic batch [batch, 3, image, image] per rank (max over ranks)."""
+    world = dist.get_world_size(group) if group is not None else 1
+    torch.manual_seed(0)
+    channels = [64, 128, 256, 512] if image == 64 else [64, 128, 256, 512, 512]       # train.py:61-70
+    model = ConvVAE(3, zdim, channels, image).to(dev)
+    opt_e = torch.optim.Adam(model.encoder.parameters(), lr=2e-4, capturable=capture)
+    opt_d = torch.optim.Adam(model.decoder.parameters(), lr=2e-4, capturable=capture)
+    exchange = None
+    if group is not None and peer:
+        from intro_tc_vae_b200.peer import PeerExchange
+        exchange = PeerExchange(batch, zdim, group, dev)
+    real = torch.rand(batch, 3, image, image, device=dev)
+    noise = torch.randn(batch, zdim, device=dev)
+    step = SoftIntroTCStep(model, opt_e, opt_d, 16704, real.shape, recon_loss_type="mse", beta_kl=0.5, beta_rec=0.75, beta_neg=512.0,
+                           gamma_r=1e-8, clip=100.0, group=group, exchange=exchange, capture=capture)
+    for _ in range(warmup):
+        out = step(real, noise)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step(real, noise)
+    e1.record()
+    torch.cuda.synchronize()
+    step.check_finite()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    return {"metric": "soft_intro_tc_train_images_per_s", "value": batch * world / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+            "ms_per_step": ms, "per_gpu_batch": batch, "image": image, "z_dim": zdim,
+            "last_losses": {k: round(v.item(), 5) for k, v in out.items()},
+            "params_M": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
+            "exchange": ("peer memory" if exchange is not None else ("nccl" if group is not None else "none")),
+            "launch": "two CUDA graphs per step (encoder phase, decoder phase), no host synchronisation" if capture else "eager",
+            "note": "fp32 (cuDNN TF32 convs as in the reference's defaults), stock torch conv modules, all loss terms through libtcelbo.so"}
 
 
 def main():
@@ -111,6 +134,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--peer", action="store_true", help="N>1: run the estimator's exchange steps over NVLink peer memory instead of NCCL")
+    ap.add_argument("--eager", action="store_true", help="issue the step eagerly instead of replaying the two captured graphs")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
@@ -119,42 +143,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
-    torch.manual_seed(0)
-    channels = [64, 128, 256, 512] if args.image == 64 else [64, 128, 256, 512, 512]       # train.py:61-70
-    model = ConvVAE(3, args.zdim, channels, args.image).to(dev)
-    opt_e = torch.optim.Adam(model.encoder.parameters(), lr=2e-4)
-    opt_d = torch.optim.Adam(model.decoder.parameters(), lr=2e-4)
-    solver = DPSolver(dataset=_Dataset(), model=model, batch_size=args.batch, optimizer_e=opt_e, optimizer_d=opt_d, recon_loss_type="mse",
-                      beta_kl=0.5, beta_rec=0.75, beta_neg=512.0, gamma_r=1e-8, device=dev, use_amp=False, grad_scaler=None,
-                      writer=None, test_iter=1000, clip=100.0)
-    solver.process_group = group
-    if group is not None and args.peer:
-        from intro_tc_vae_b200.peer import PeerExchange
-        solver.peer_exchange = PeerExchange(args.batch, args.zdim, group, dev)
-    batch = torch.rand(args.batch, 3, args.image, args.image, device=dev)
-    out = None
-    for it in range(args.warmup):
-        out = solver.train_step(batch, it)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for it in range(args.steps):
-        out = solver.train_step(batch, args.warmup + it)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    line = measure(args.image, args.zdim, args.batch, args.steps, args.warmup, dev, group, args.peer, capture=not args.eager)
     if rank == 0:
-        print(json.dumps({"metric": "soft_intro_tc_train_images_per_s", "value": args.batch * world / (t.item() * 1e-3), "unit": "images/s",
-                          "n_gpus": world, "ms_per_step": t.item(), "per_gpu_batch": args.batch, "image": args.image, "z_dim": args.zdim,
-                          "last_losses": {k: (round(v, 5) if v is not None else None) for k, v in out.items()},
-                          "params_M": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
-                          "exchange": ("peer memory" if (group is not None and args.peer) else ("nccl" if group is not None else "none")),
-                          "note": "fp32 (TF32 convs off), stock torch conv modules, all loss terms through libtcelbo.so, eager launches"}), flush=True)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         os._exit(0)
