@@ -172,7 +172,8 @@ int tcelbo_klloss_backward_ex(const float* z, int64_t ldz, const float* mu_all, 
  *             scratch buffers of all ranks (`scratch_parts`, DEVICE array of n_ranks scratch base pointers) and writes
  *             grad_z, grad_logvar and grad_mu_loc [b_loc, d] (the already reduce-scattered gradient of mu, KL term included).
  * A scratch (and a published mu buffer) may be reused two exchanges later (double-buffer them), never by the very next one.
- * `mu_loc` is this rank's rows of mu (the KL term reads it).  Row-variance density only.
+ * `mu_loc` is this rank's rows of mu (the KL term reads it).  Row-variance density only.  `fusion` as in the _ex entry points
+ * (NULL = none): with `eps`, z is formed in the prologue and grad_mu_loc / grad_logvar are the gradients w.r.t. the encoder outputs.
  */
 #define TCELBO_PEER_SWEEP  1
 #define TCELBO_PEER_FINISH 2
@@ -180,14 +181,14 @@ int tcelbo_klloss_forward_peer(const float* z, int64_t ldz, const float* mu_loc,
                                const float* const* mu_parts, int64_t ld_part, const float* logvar, int64_t ldlv,
                                int b_loc, int n_ranks, int rank, int d, int64_t dataset_size, uint32_t flags, float beta,
                                float* loss_rows, float* kl_rows, float* log_qz, float* log_qz_prod,
-                               void* workspace, size_t workspace_bytes, void* stream);
+                               const tcelbo_fusion* fusion, void* workspace, size_t workspace_bytes, void* stream);
 int tcelbo_klloss_backward_peer(int phase, const float* z, int64_t ldz, const float* mu_loc, int64_t ldmu,
                                 const float* logvar, int64_t ldlv, int b_loc, int n_ranks, int rank, int d,
                                 int64_t dataset_size, uint32_t flags, float beta,
                                 const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
                                 float* grad_z, int64_t ldgz, float* grad_mu_loc, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
                                 const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
-                                const void* const* scratch_parts, void* stream);
+                                const void* const* scratch_parts, const tcelbo_fusion* fusion, void* stream);
 
 /* kl_rows[i] = -0.5 * sum_d (1 + logvar - exp(logvar) - mu^2)   (ops.py:161-163; argument order logvar, mu) */
 int tcelbo_kl_forward(const float* logvar, int64_t ldlv, const float* mu, int64_t ldmu,

@@ -363,11 +363,12 @@ int tcelbo_klloss_backward_ex(const float* z, int64_t ldz, const float* mu_all, 
 int tcelbo_klloss_forward_peer(const float* z, int64_t ldz, const float* mu_loc, int64_t ldmu, const float* const* mu_parts, int64_t ld_part,
                                const float* logvar, int64_t ldlv, int b_loc, int n_ranks, int rank, int d, int64_t dataset_size,
                                uint32_t flags, float beta, float* loss_rows, float* kl_rows, float* log_qz, float* log_qz_prod,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+                               const tcelbo_fusion* fusion, void* workspace, size_t workspace_bytes, void* stream) {
     if (!loss_rows || !kl_rows || !mu_parts) return fail(TCELBO_ERR_INVALID, "null pointer");
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks || ld_part < d) return fail(TCELBO_ERR_INVALID, "bad rank / n_ranks / ld_part");
     if ((int64_t)b_loc * n_ranks > INT32_MAX) return fail(TCELBO_ERR_INVALID, "global batch too large");
     LossFusion lf; lf.on = true; lf.beta = beta; lf.loss_rows = loss_rows; lf.kl_rows = kl_rows;
+    if (fusion) lf.fz = *fusion;
     Peers peers; peers.mu_parts = mu_parts; peers.ld_part = ld_part; peers.n_ranks = n_ranks;
     return forward_impl(z, ldz, mu_loc, ldmu, logvar, ldlv, b_loc, b_loc * n_ranks, rank * b_loc, d, dataset_size, flags,
                         log_qz, log_qz_prod, lf, workspace, workspace_bytes, stream, peers);
@@ -378,13 +379,15 @@ int tcelbo_klloss_backward_peer(int phase, const float* z, int64_t ldz, const fl
                                 const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
                                 float* grad_z, int64_t ldgz, float* grad_mu_loc, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
                                 const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
-                                const void* const* scratch_parts, void* stream) {
-    if (!g_loss_rows) return fail(TCELBO_ERR_INVALID, "null upstream gradient pointer");
+                                const void* const* scratch_parts, const tcelbo_fusion* fusion, void* stream) {
+    if (!g_loss_rows && !(fusion && (fusion->g_loss_mean || fusion->g_expelbo || fusion->g_kl_mean)) && !g_kl_rows && !g_log_qz && !g_log_qz_prod)
+        return fail(TCELBO_ERR_INVALID, "no upstream gradient given");
     if (phase != TCELBO_PEER_SWEEP && phase != TCELBO_PEER_FINISH) return fail(TCELBO_ERR_INVALID, "phase must be TCELBO_PEER_SWEEP or TCELBO_PEER_FINISH");
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(TCELBO_ERR_INVALID, "bad rank / n_ranks");
     if (phase == TCELBO_PEER_FINISH && !scratch_parts) return fail(TCELBO_ERR_INVALID, "null scratch table");
     if ((int64_t)b_loc * n_ranks > INT32_MAX) return fail(TCELBO_ERR_INVALID, "global batch too large");
     LossFusion lf; lf.on = true; lf.beta = beta; lf.g_loss = g_loss_rows; lf.g_kl = g_kl_rows;
+    if (fusion) lf.fz = *fusion;
     Peers peers; peers.scratch_parts = scratch_parts; peers.n_ranks = n_ranks; peers.phase = phase;
     return backward_impl(z, ldz, mu_loc, ldmu, logvar, ldlv, b_loc, b_loc * n_ranks, rank * b_loc, d, dataset_size, flags,
                          g_log_qz, g_log_qz_prod, lf, grad_z, ldgz, grad_mu_loc, ldgmu, grad_logvar, ldglv,

@@ -176,28 +176,27 @@ class GraphedKLLoss:
                 if self._gmu_all is not None:
                     dist.reduce_scatter_tensor(self.dmu, self._gmu_all, op=dist.ReduceOp.SUM, group=group)
                 return self._loss
-            # peer-memory exchange: the library's prep / finalize kernels gather mu and reduce-scatter its gradient over NVLink
-            _lib.check(lib.tcelbo_reparam_forward(P(mu), d, P(lv), d, P(eps), d, b_loc, d, P(z), d, st), "tcelbo_reparam_forward")
+            # peer-memory exchange: the library's prologue / finalize kernels gather mu and reduce-scatter its gradient over NVLink;
+            # reparameterize and the batch mean are fused here too (publish copy, barrier, 3 + barrier + 3 launches)
             k = exch.next_forward()
             exch.mu_sym[k].copy_(mu)
             exch.mu_hdl.barrier(channel=0)
-            _lib.check(lib.tcelbo_klloss_forward_peer(P(z), d, P(mu), d, P(exch.mu_tables[k]), d, P(lv), d, b_loc, self.world,
-                                                      self.rank, d, n, flags, beta, *rows, P(self._ws), self._ws.numel(), st),
+            fz = _lib.Fusion(eps=P(eps), ldeps=d, z_out=P(z), ldz_out=d, loss_mean=P(self._loss))
+            _lib.check(lib.tcelbo_klloss_forward_peer(None, 0, P(mu), d, P(exch.mu_tables[k]), d, P(lv), d, b_loc, self.world,
+                                                      self.rank, d, n, flags, beta, *rows, ctypes.byref(fz), P(self._ws), self._ws.numel(), st),
                        "tcelbo_klloss_forward_peer")
-            loss = self._rows[0].mean()
             k = exch.next_backward()
             scratch = exch.scratch_sym[k]
+            fb = _lib.Fusion(eps=P(eps), ldeps=d, g_loss_mean=P(self._one))
             for phase in (_lib.PEER_SWEEP, _lib.PEER_FINISH):
-                _lib.check(lib.tcelbo_klloss_backward_peer(phase, P(z), d, P(mu), d, P(lv), d, b_loc, self.world, self.rank, d, n,
-                                                           flags, beta, P(self._g_loss), None, None, None,
+                _lib.check(lib.tcelbo_klloss_backward_peer(phase, None, 0, P(mu), d, P(lv), d, b_loc, self.world, self.rank, d, n,
+                                                           flags, beta, None, None, None, None,
                                                            P(self._gz), d, P(self.dmu), d, P(self.dlogvar), d,
                                                            P(self._ws), self._ws.numel(), P(scratch), exch.scratch_bytes,
-                                                           P(exch.scratch_tables[k]), st), "tcelbo_klloss_backward_peer")
+                                                           P(exch.scratch_tables[k]), ctypes.byref(fb), st), "tcelbo_klloss_backward_peer")
                 if phase == _lib.PEER_SWEEP:
                     exch.scratch_hdl.barrier(channel=0)
-            _lib.check(lib.tcelbo_reparam_backward_acc(P(lv), d, P(eps), d, P(self._gz), d, b_loc, d, P(self.dmu), d,
-                                                       P(self.dlogvar), d, st), "tcelbo_reparam_backward_acc")
-        return loss
+        return self._loss
 
     def __call__(self, mu: Tensor, logvar: Tensor, eps: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         with torch.no_grad():

@@ -111,7 +111,7 @@ class _PeerKLLoss(torch.autograd.Function):
                                                 exch.mu_tables[k].data_ptr(), d, logvar.data_ptr(), logvar.stride(0),
                                                 b_loc, exch.world, exch.rank, d, dataset_size, flags, beta,
                                                 out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
-                                                ws.data_ptr(), nbytes, _stream(z))
+                                                None, ws.data_ptr(), nbytes, _stream(z))
         _lib.check(st, "tcelbo_klloss_forward_peer")
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(z, mu, logvar, ws)
@@ -147,7 +147,7 @@ class _PeerKLLoss(torch.autograd.Function):
                 g_loss.data_ptr(), *(t.data_ptr() if t is not None else None for t in opt),
                 grad_z.data_ptr(), d, grad_mu.data_ptr(), d, grad_lv.data_ptr(), d,
                 ws.data_ptr(), ws.numel(), scratch.data_ptr(), exch.scratch_bytes,
-                exch.scratch_tables[k].data_ptr(), _stream(z))
+                exch.scratch_tables[k].data_ptr(), None, _stream(z))
 
         with torch.cuda.device(z.device):
             _lib.check(call(_lib.PEER_SWEEP), "tcelbo_klloss_backward_peer(sweep)")
