@@ -320,8 +320,8 @@ def run_ours(args):
     t_wall1 = time.perf_counter()
     launches = lib.tcelbo_launch_count() - launches0
     if graphed is not None:                                # replayed launches do not pass through the host-side counter:
-        c0 = lib.tcelbo_launch_count()                     # count the kernels of one eager step (same kernels as the graph)
-        step(mu, lv, eps)
+        c0 = lib.tcelbo_launch_count()                     # count the kernels of one eager issue of the captured step function
+        graphed._step()
         torch.cuda.synchronize()
         launches = (lib.tcelbo_launch_count() - c0) * args.steps
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
@@ -445,7 +445,7 @@ def run_ours(args):
         traffic = None                                         # dram bytes per launch of the dominant kernel, from the committed ncu capture
         try:
             import csv
-            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_final_raw.csv"))))
+            rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r2_ncu_full_raw.csv"))))
             hdr, units = rows[0], rows[1]
             ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -457,7 +457,7 @@ def run_ours(args):
         roof = {
             "bound": "sfu", "kernel": dom, "achieved": achieved / 1e9, "peak": peak_nominal / 1e9, "unit": "Gex2/s",
             "frac": achieved / peak_nominal, "traffic": traffic,
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel (bytes, profiles/r1_ncu_full_final_raw.csv, N=1 shape)",
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel (bytes, profiles/r2_ncu_full_raw.csv, N=1 shape)",
             "peak_note": "148 SM x 16 MUFU/clk x 1.965 GHz (max SM clock); ex2_measured_gps is the in-job saturation probe",
             "ex2_measured_gps": ex2_measured / 1e9, "frac_of_measured_ex2": achieved / ex2_measured,
             "peak_at_observed_clock_gps": peak_at_clock / 1e9,

@@ -175,20 +175,35 @@ int tcelbo_klloss_backward_ex(const float* z, int64_t ldz, const float* mu_all, 
  * `mu_loc` is this rank's rows of mu (the KL term reads it).  Row-variance density only.  `fusion` as in the _ex entry points
  * (NULL = none): with `eps`, z is formed in the prologue and grad_mu_loc / grad_logvar are the gradients w.r.t. the encoder outputs.
  */
+/* Optional in-kernel barriers for the two exchange steps (NULL: the CALLER puts a cross-rank barrier on the stream before
+ * tcelbo_klloss_forward_peer and before the TCELBO_PEER_FINISH call, as described above).  With it, the prologue kernel signals
+ * "my rows are published" to every rank and waits for all ranks before it gathers (its row work overlaps the wait), and the
+ * finalize kernel does the same for "my sweep is done" before it reduces: no barrier launches at all.  Every rank must then
+ * issue the same sequence of peer calls; a rank that never arrives makes the others trap after ~2 s.
+ *   flag_parts  DEVICE table of n_ranks pointers; entry r = rank r's flag array of 2*n_ranks 32-bit words, zero-initialised
+ *               once (before the first call, with a real barrier after the zeroing), mapped into every process
+ *   state       DEVICE, local to this rank: 4 zero-initialised 32-bit words (barrier epochs and CTA tickets) */
+typedef struct tcelbo_peer_sync {
+    unsigned int* const* flag_parts;
+    unsigned int* state;
+} tcelbo_peer_sync;
+
 #define TCELBO_PEER_SWEEP  1
 #define TCELBO_PEER_FINISH 2
 int tcelbo_klloss_forward_peer(const float* z, int64_t ldz, const float* mu_loc, int64_t ldmu,
                                const float* const* mu_parts, int64_t ld_part, const float* logvar, int64_t ldlv,
                                int b_loc, int n_ranks, int rank, int d, int64_t dataset_size, uint32_t flags, float beta,
                                float* loss_rows, float* kl_rows, float* log_qz, float* log_qz_prod,
-                               const tcelbo_fusion* fusion, void* workspace, size_t workspace_bytes, void* stream);
+                               const tcelbo_fusion* fusion, const tcelbo_peer_sync* sync,
+                               void* workspace, size_t workspace_bytes, void* stream);
 int tcelbo_klloss_backward_peer(int phase, const float* z, int64_t ldz, const float* mu_loc, int64_t ldmu,
                                 const float* logvar, int64_t ldlv, int b_loc, int n_ranks, int rank, int d,
                                 int64_t dataset_size, uint32_t flags, float beta,
                                 const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
                                 float* grad_z, int64_t ldgz, float* grad_mu_loc, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
                                 const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
-                                const void* const* scratch_parts, const tcelbo_fusion* fusion, void* stream);
+                                const void* const* scratch_parts, const tcelbo_fusion* fusion, const tcelbo_peer_sync* sync,
+                                void* stream);
 
 /* kl_rows[i] = -0.5 * sum_d (1 + logvar - exp(logvar) - mu^2)   (ops.py:161-163; argument order logvar, mu) */
 int tcelbo_kl_forward(const float* logvar, int64_t ldlv, const float* mu, int64_t ldmu,

@@ -25,6 +25,11 @@ ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 1, 2, 3, 4
 _f = c_void_p          # device pointers are passed as integers (tensor.data_ptr())
 
 
+class PeerSyncArgs(ctypes.Structure):
+    """``tcelbo_peer_sync`` of include/tcelbo.h: in-kernel cross-rank barriers of the peer-memory exchange."""
+    _fields_ = [("flag_parts", c_void_p), ("state", c_void_p)]
+
+
 class Fusion(ctypes.Structure):
     """``tcelbo_fusion`` of include/tcelbo.h: optional prologue / epilogue fusions of the fused loss (None = off)."""
     _fields_ = [("eps", c_void_p), ("ldeps", c_int64), ("z_out", c_void_p), ("ldz_out", c_int64),
@@ -54,10 +59,10 @@ _SIGNATURES = {
                                           _f, _f, _f, _f, POINTER(Fusion), _f, c_int64, _f, c_int64, _f, c_int64, c_void_p, c_size_t,
                                           c_void_p, c_size_t, c_void_p]),
     "tcelbo_klloss_forward_peer": (c_int, [_f, c_int64, _f, c_int64, c_void_p, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64,
-                                           c_uint32, c_float, _f, _f, _f, _f, POINTER(Fusion), c_void_p, c_size_t, c_void_p]),
+                                           c_uint32, c_float, _f, _f, _f, _f, POINTER(Fusion), POINTER(PeerSyncArgs), c_void_p, c_size_t, c_void_p]),
     "tcelbo_klloss_backward_peer": (c_int, [c_int, _f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, c_int, c_int, c_int64, c_uint32,
                                             c_float, _f, _f, _f, _f, _f, c_int64, _f, c_int64, _f, c_int64, c_void_p, c_size_t,
-                                            c_void_p, c_size_t, c_void_p, POINTER(Fusion), c_void_p]),
+                                            c_void_p, c_size_t, c_void_p, POINTER(Fusion), POINTER(PeerSyncArgs), c_void_p]),
     "tcelbo_kl_forward": (c_int, [_f, c_int64, _f, c_int64, c_int, c_int, _f, c_void_p]),
     "tcelbo_kl_backward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int, c_int, _f, c_int64, _f, c_int64, c_void_p]),
     "tcelbo_reparam_forward": (c_int, [_f, c_int64, _f, c_int64, _f, c_int64, c_int, c_int, _f, c_int64, c_void_p]),

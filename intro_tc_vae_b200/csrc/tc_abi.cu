@@ -130,6 +130,7 @@ struct Peers {
     const void* const* scratch_parts = nullptr;                    // backward finish: device table of every rank's scratch base
     int n_ranks = 0;
     int phase = 3;                                                 // backward: 1 = sweep into scratch, 2 = finish from the peers' scratch
+    PeerSync sync = {nullptr, nullptr, 0, 0, 0};                   // in-kernel barrier (tcelbo_peer_sync) instead of the caller's
     bool on() const { return n_ranks > 0; }
 };
 
@@ -175,6 +176,7 @@ static int forward_impl(const float* z, int64_t ldz, const float* mu_all, int64_
         pa.logvar = logvar; pa.ldlv = ldlv;
         pa.b_loc = b_loc; pa.b_glob = b_glob; pa.d = d; pa.bl_pad = p.bl_pad; pa.bg_pad = p.bg_pad; pa.dp = p.dp;
         pa.mu_pad = mu_pad; pa.zs = zs; pa.ns = ns; pa.qmax = qmax; pa.shift = shift; pa.vr = vr; pa.ticket = ticket;
+        pa.sync = peers.sync;
         if ((e = launch_prep(pa, st)) != cudaSuccess) return fail_cuda(e, "prep");
     }
 
@@ -273,6 +275,7 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
     fa.gk = lf.on ? gk : nullptr; fa.lv = logvar; fa.ldlv = ldlv; fa.mu_all = mu_all; fa.ldmu = ldmu; fa.row_offset = row_offset;
     fa.scratch_parts = peers.on() ? peers.scratch_parts : nullptr; fa.g_off = p.boff_G; fa.n_ranks = peers.n_ranks;
     fa.eps = lf.fz.eps; fa.ldeps = lf.fz.ldeps;
+    fa.sync = peers.sync;
 
     BwdFusedArgs ua;
     ua.zs = zs; ua.ns = ns; ua.qmax = qmax; ua.gps = gps; ua.gj = gj; ua.J2 = J2; ua.mu_pad = mu_pad;
@@ -363,13 +366,15 @@ int tcelbo_klloss_backward_ex(const float* z, int64_t ldz, const float* mu_all, 
 int tcelbo_klloss_forward_peer(const float* z, int64_t ldz, const float* mu_loc, int64_t ldmu, const float* const* mu_parts, int64_t ld_part,
                                const float* logvar, int64_t ldlv, int b_loc, int n_ranks, int rank, int d, int64_t dataset_size,
                                uint32_t flags, float beta, float* loss_rows, float* kl_rows, float* log_qz, float* log_qz_prod,
-                               const tcelbo_fusion* fusion, void* workspace, size_t workspace_bytes, void* stream) {
+                               const tcelbo_fusion* fusion, const tcelbo_peer_sync* sync, void* workspace, size_t workspace_bytes, void* stream) {
     if (!loss_rows || !kl_rows || !mu_parts) return fail(TCELBO_ERR_INVALID, "null pointer");
+    if (sync && (!sync->flag_parts || !sync->state)) return fail(TCELBO_ERR_INVALID, "peer_sync needs the flag table and the state words");
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks || ld_part < d) return fail(TCELBO_ERR_INVALID, "bad rank / n_ranks / ld_part");
     if ((int64_t)b_loc * n_ranks > INT32_MAX) return fail(TCELBO_ERR_INVALID, "global batch too large");
     LossFusion lf; lf.on = true; lf.beta = beta; lf.loss_rows = loss_rows; lf.kl_rows = kl_rows;
     if (fusion) lf.fz = *fusion;
     Peers peers; peers.mu_parts = mu_parts; peers.ld_part = ld_part; peers.n_ranks = n_ranks;
+    if (sync) peers.sync = PeerSync{sync->flag_parts, sync->state, 0, rank, n_ranks};
     return forward_impl(z, ldz, mu_loc, ldmu, logvar, ldlv, b_loc, b_loc * n_ranks, rank * b_loc, d, dataset_size, flags,
                         log_qz, log_qz_prod, lf, workspace, workspace_bytes, stream, peers);
 }
@@ -379,7 +384,8 @@ int tcelbo_klloss_backward_peer(int phase, const float* z, int64_t ldz, const fl
                                 const float* g_loss_rows, const float* g_kl_rows, const float* g_log_qz, const float* g_log_qz_prod,
                                 float* grad_z, int64_t ldgz, float* grad_mu_loc, int64_t ldgmu, float* grad_logvar, int64_t ldglv,
                                 const void* workspace, size_t workspace_bytes, void* scratch, size_t scratch_bytes,
-                                const void* const* scratch_parts, const tcelbo_fusion* fusion, void* stream) {
+                                const void* const* scratch_parts, const tcelbo_fusion* fusion, const tcelbo_peer_sync* sync, void* stream) {
+    if (sync && (!sync->flag_parts || !sync->state)) return fail(TCELBO_ERR_INVALID, "peer_sync needs the flag table and the state words");
     if (!g_loss_rows && !(fusion && (fusion->g_loss_mean || fusion->g_expelbo || fusion->g_kl_mean)) && !g_kl_rows && !g_log_qz && !g_log_qz_prod)
         return fail(TCELBO_ERR_INVALID, "no upstream gradient given");
     if (phase != TCELBO_PEER_SWEEP && phase != TCELBO_PEER_FINISH) return fail(TCELBO_ERR_INVALID, "phase must be TCELBO_PEER_SWEEP or TCELBO_PEER_FINISH");
@@ -389,6 +395,7 @@ int tcelbo_klloss_backward_peer(int phase, const float* z, int64_t ldz, const fl
     LossFusion lf; lf.on = true; lf.beta = beta; lf.g_loss = g_loss_rows; lf.g_kl = g_kl_rows;
     if (fusion) lf.fz = *fusion;
     Peers peers; peers.scratch_parts = scratch_parts; peers.n_ranks = n_ranks; peers.phase = phase;
+    if (sync) peers.sync = PeerSync{sync->flag_parts, sync->state, 1, rank, n_ranks};
     return backward_impl(z, ldz, mu_loc, ldmu, logvar, ldlv, b_loc, b_loc * n_ranks, rank * b_loc, d, dataset_size, flags,
                          g_log_qz, g_log_qz_prod, lf, grad_z, ldgz, grad_mu_loc, ldgmu, grad_logvar, ldglv,
                          workspace, workspace_bytes, scratch, scratch_bytes, stream, peers);

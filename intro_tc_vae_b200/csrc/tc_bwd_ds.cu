@@ -385,6 +385,7 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
     const int64_t n_col = a.scratch_parts != nullptr ? 0 : (int64_t)a.b_glob * a.d;
     const size_t split_stride = (size_t)a.bl_pad * a.dp;
     const bool rows_own_mu = a.scratch_parts != nullptr || a.eps != nullptr;   // the row threads also write grad_mu of the local rows
+    if (a.scratch_parts != nullptr && a.sync.on()) peer_barrier(a.sync);        // every rank's sweep has finished: their column sums are final
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_row + n_col; idx += (int64_t)gridDim.x * blockDim.x) {
         if (idx < n_row) {
             const int i = (int)(idx / a.d), dd = (int)(idx % a.d);
@@ -448,6 +449,7 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
             a.grad_mu[(int64_t)j * a.ldgmu + dd] = g;
         }
     }
+    if (a.scratch_parts != nullptr && a.sync.on()) peer_barrier_done(a.sync);
 }
 
 // variant 0 is the shipped configuration; the others are tuning points kept for tools/tune_bwd.py (profiles/r2_bwd_ds_sweep.md)

@@ -118,6 +118,52 @@ __device__ __forceinline__ void weight_of(const Weights& w, int i_glob, int j, f
     if (j >= w.b_glob) { rho = 0.0f; l2rho = -INFINITY; }
 }
 
+// ---- cross-rank barrier inside a kernel, over peer-mapped flags (one process per GPU, NVLink) --------------------
+// Rank r owns a flag array of n_channels * n_ranks words in memory every rank has mapped.  Barrier number e+1 of a channel:
+// every rank stores e+1 into slot [channel][its rank] of EVERY rank's array (release, system scope) and then waits until all
+// n_ranks slots of its own array have reached e+1 (acquire).  `epoch` (local) counts the barriers this rank has completed on
+// the channel; it is advanced by the last CTA of the kernel to leave, so every CTA of one launch reads the same value.
+// Kernels that use this must be launched by all ranks in the same order; a rank that never arrives traps the others after
+// ~2 s instead of hanging the GPUs.
+struct PeerSync {
+    unsigned int* const* flag_parts;   // device table [n_ranks] of the ranks' flag arrays (nullptr: no in-kernel barrier)
+    unsigned int* state;               // local, zero-initialised: [2*channel] = epoch, [2*channel+1] = CTA ticket
+    int channel, rank, n_ranks;
+    __device__ __forceinline__ bool on() const { return flag_parts != nullptr; }
+};
+
+// one CTA signals (first n_ranks threads), every CTA waits; call with all threads of the CTA
+__device__ __forceinline__ void peer_barrier(const PeerSync& ps) {
+    const unsigned int want = *reinterpret_cast<volatile unsigned int*>(ps.state + 2 * ps.channel) + 1u;
+    if ((int)threadIdx.x < ps.n_ranks) {
+        if (blockIdx.x == 0) {
+            unsigned int* dst = ps.flag_parts[threadIdx.x] + ps.channel * ps.n_ranks + ps.rank;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(dst), "r"(want) : "memory");
+        }
+        const unsigned int* src = ps.flag_parts[ps.rank] + ps.channel * ps.n_ranks + threadIdx.x;
+        const long long t0 = clock64();
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            if ((int)(v - want) < 0 && clock64() - t0 > 4000000000ll) __trap();
+        } while ((int)(v - want) < 0);
+    }
+    __syncthreads();
+}
+
+// at the very end of the kernel, all threads: the last CTA to leave publishes the new epoch and resets the ticket
+__device__ __forceinline__ void peer_barrier_done(const PeerSync& ps) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ps.state + 2 * ps.channel + 1, 1u) == gridDim.x - 1) {
+            ps.state[2 * ps.channel + 1] = 0u;
+            __threadfence();
+            atomicAdd(ps.state + 2 * ps.channel, 1u);
+        }
+    }
+}
+
 // online logsumexp in base 2: (m, s) <- (m, s) (+) 2^x
 __device__ __forceinline__ void lse2_push(float& m, float& s, float x) {
     const float mn = fmaxf(m, x);

@@ -23,48 +23,50 @@ template <bool kParts>
 __global__ void prep_kernel(const PrepArgs a) {
     const int64_t n_col = (int64_t)a.bg_pad * a.dp, n_row = (int64_t)a.bl_pad * a.dp;
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket = 0u;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_col + n_row; idx += (int64_t)gridDim.x * blockDim.x) {
-        if (idx < n_col) {
-            // column operand, padded; with kParts the rows of mu live in `rows_per_part`-row blocks of different allocations (one
-            // per rank, peer-mapped): the all-gather of the column operand is this kernel's load phase (128-byte reads over NVLink)
-            const int j = (int)(idx / a.dp), dd = (int)(idx % a.dp);
-            float v = 0.0f;
-            if (j < a.b_glob && dd < a.d) {
-                if (kParts) {
-                    const int part = j / a.rows_per_part;
-                    v = *static_cast<const volatile float*>(a.parts[part] + (int64_t)(j - part * a.rows_per_part) * a.ld_part + dd);   // no L1 / nc path
-                } else {
-                    v = a.mu_all[(int64_t)j * a.ldmu + dd];
-                }
+    // ---- rows first (local data only): per-(i,d) constants, optionally the fused reparameterize
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_row; k += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(k / a.dp), dd = (int)(k % a.dp);
+        float o_zs = 0.f, o_ns = 0.f, o_q = 0.f, o_sh = 0.f, o_vr = 0.f;
+        if (i < a.b_loc && dd < a.d) {
+            const float lv = a.logvar[(int64_t)i * a.ldlv + dd];
+            float zv;
+            if (a.eps != nullptr) {                                     // fused reparameterize, ops.py:183-185
+                zv = a.mu_loc[(int64_t)i * a.ldmu_loc + dd] + a.eps[(int64_t)i * a.ldeps + dd] * expf(0.5f * lv);
+                if (a.z_out != nullptr) a.z_out[(int64_t)i * a.ldz_out + dd] = zv;
+            } else {
+                zv = a.z[(int64_t)i * a.ldz + dd];
             }
-            a.mu_pad[idx] = v;
-        } else {
-            const int64_t k = idx - n_col;
-            const int i = (int)(k / a.dp), dd = (int)(k % a.dp);
-            float o_zs = 0.f, o_ns = 0.f, o_q = 0.f, o_sh = 0.f, o_vr = 0.f;
-            if (i < a.b_loc && dd < a.d) {
-                const float lv = a.logvar[(int64_t)i * a.ldlv + dd];
-                float zv;
-                if (a.eps != nullptr) {                                     // fused reparameterize, ops.py:183-185
-                    zv = a.mu_loc[(int64_t)i * a.ldmu_loc + dd] + a.eps[(int64_t)i * a.ldeps + dd] * expf(0.5f * lv);
-                    if (a.z_out != nullptr) a.z_out[(int64_t)i * a.ldz_out + dd] = zv;
-                } else {
-                    zv = a.z[(int64_t)i * a.ldz + dd];
-                }
-                const float var = expf(lv);
-                const float vc = (var < kVarFloor) ? kVarFloor : var;       // NaN stays NaN, like clamp_
-                const float iv = 1.0f / vc;
-                const float c = -0.5f * (logf(vc) + kLog2Pi);
-                const float sc = sqrtf(0.5f * kLog2e * iv);
-                o_zs = zv * sc;
-                o_ns = -sc;
-                o_q = fmaxf(0.0f, (50.0f + c) * kLog2e);
-                o_sh = (c < kLogpFloor) ? kLogpFloor : c;
-                o_vr = 0.5f * var * iv;                                     // straight-through floor: d/dlv uses the unclamped var
-            }
-            a.zs[k] = o_zs; a.ns[k] = o_ns; a.qmax[k] = o_q; a.shift[k] = o_sh; a.vr[k] = o_vr;
+            const float var = expf(lv);
+            const float vc = (var < kVarFloor) ? kVarFloor : var;       // NaN stays NaN, like clamp_
+            const float iv = 1.0f / vc;
+            const float c = -0.5f * (logf(vc) + kLog2Pi);
+            const float sc = sqrtf(0.5f * kLog2e * iv);
+            o_zs = zv * sc;
+            o_ns = -sc;
+            o_q = fmaxf(0.0f, (50.0f + c) * kLog2e);
+            o_sh = (c < kLogpFloor) ? kLogpFloor : c;
+            o_vr = 0.5f * var * iv;                                     // straight-through floor: d/dlv uses the unclamped var
         }
+        a.zs[k] = o_zs; a.ns[k] = o_ns; a.qmax[k] = o_q; a.shift[k] = o_sh; a.vr[k] = o_vr;
     }
+    // ---- columns, padded.  With kParts the rows of mu live in `rows_per_part`-row blocks of different allocations (one per rank,
+    //      peer-mapped): the all-gather of the column operand is this kernel's load phase (128-byte reads over NVLink), after
+    //      the in-kernel barrier that tells every rank's block is published (the row work above overlaps the wait)
+    if (kParts && a.sync.on()) peer_barrier(a.sync);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_col; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / a.dp), dd = (int)(idx % a.dp);
+        float v = 0.0f;
+        if (j < a.b_glob && dd < a.d) {
+            if (kParts) {
+                const int part = j / a.rows_per_part;
+                v = *static_cast<const volatile float*>(a.parts[part] + (int64_t)(j - part * a.rows_per_part) * a.ld_part + dd);   // no L1 / nc path
+            } else {
+                v = a.mu_all[(int64_t)j * a.ldmu + dd];
+            }
+        }
+        a.mu_pad[idx] = v;
+    }
+    if (kParts && a.sync.on()) peer_barrier_done(a.sync);
 }
 
 // =====================================================================================================

@@ -45,6 +45,7 @@ struct PrepArgs {
     int b_loc, b_glob, d, bl_pad, bg_pad, dp;
     float* mu_pad; float* zs; float* ns; float* qmax; float* shift; float* vr;
     unsigned int* ticket;
+    PeerSync sync;                                               // peer exchange: barrier between the ranks' publish and this gather
 };
 
 struct BwdFusedArgs {
@@ -77,6 +78,7 @@ struct BwdFinArgs {
     // fused reparameterize backward (ops.py:183-185): with eps set, the local rows of grad_mu also receive grad_z and grad_lv
     // receives grad_z * eps * 0.5 * exp(logvar / 2), i.e. the outputs are the gradients w.r.t. the encoder's mu / logvar
     const float* eps; int64_t ldeps;
+    PeerSync sync;                                               // peer exchange: barrier between the ranks' sweeps and this reduce
 };
 
 cudaError_t launch_prep(const PrepArgs& a, cudaStream_t st);

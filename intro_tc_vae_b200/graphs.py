@@ -180,10 +180,10 @@ class GraphedKLLoss:
             # reparameterize and the batch mean are fused here too (publish copy, barrier, 3 + barrier + 3 launches)
             k = exch.next_forward()
             exch.mu_sym[k].copy_(mu)
-            exch.mu_hdl.barrier(channel=0)
+            exch.barrier_forward()
             fz = _lib.Fusion(eps=P(eps), ldeps=d, z_out=P(z), ldz_out=d, loss_mean=P(self._loss))
             _lib.check(lib.tcelbo_klloss_forward_peer(None, 0, P(mu), d, P(exch.mu_tables[k]), d, P(lv), d, b_loc, self.world,
-                                                      self.rank, d, n, flags, beta, *rows, ctypes.byref(fz), P(self._ws), self._ws.numel(), st),
+                                                      self.rank, d, n, flags, beta, *rows, ctypes.byref(fz), exch.sync_arg(), P(self._ws), self._ws.numel(), st),
                        "tcelbo_klloss_forward_peer")
             k = exch.next_backward()
             scratch = exch.scratch_sym[k]
@@ -193,9 +193,10 @@ class GraphedKLLoss:
                                                            flags, beta, None, None, None, None,
                                                            P(self._gz), d, P(self.dmu), d, P(self.dlogvar), d,
                                                            P(self._ws), self._ws.numel(), P(scratch), exch.scratch_bytes,
-                                                           P(exch.scratch_tables[k]), ctypes.byref(fb), st), "tcelbo_klloss_backward_peer")
+                                                           P(exch.scratch_tables[k]), ctypes.byref(fb), exch.sync_arg(), st),
+                           "tcelbo_klloss_backward_peer")
                 if phase == _lib.PEER_SWEEP:
-                    exch.scratch_hdl.barrier(channel=0)
+                    exch.barrier_backward()
         return self._loss
 
     def __call__(self, mu: Tensor, logvar: Tensor, eps: Tensor) -> Tuple[Tensor, Tensor, Tensor]:

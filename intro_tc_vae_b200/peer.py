@@ -65,8 +65,33 @@ class PeerExchange:
                                            device=self.device) for k in range(2)]
             self.scratch_tables = [torch.tensor([int(p) + k * pitch for p in self.scratch_hdl.buffer_ptrs], dtype=torch.int64,
                                                 device=self.device) for k in range(2)]
+            # in-kernel barriers (tcelbo_peer_sync): 2 channels x world flag words per rank in symmetric memory, 4 local state words
+            self.flags_sym = symm.empty(2 * self.world, dtype=torch.int32, device=self.device)
+            self.flags_sym.zero_()
+            self.flags_hdl = symm.rendezvous(self.flags_sym, name)
+            self.flag_table = torch.tensor([int(p) for p in self.flags_hdl.buffer_ptrs], dtype=torch.int64, device=self.device)
+            self.sync_state = torch.zeros(4, dtype=torch.int32, device=self.device)
+            torch.cuda.synchronize(self.device)
+            self.flags_hdl.barrier(channel=0)                       # every rank's flags are zero before anyone signals
+            torch.cuda.synchronize(self.device)
+        import os
+        self.inkernel_sync = os.environ.get("TCELBO_PEER_SYNC", "kernel") != "host"
+        self._sync_args = _lib.PeerSyncArgs(flag_parts=self.flag_table.data_ptr(), state=self.sync_state.data_ptr())
         self._n_fwd = 0
         self._n_bwd = 0
+
+    def sync_arg(self):
+        """ctypes pointer to the tcelbo_peer_sync of this exchange, or None when the host-side barriers are used."""
+        import ctypes
+        return ctypes.byref(self._sync_args) if self.inkernel_sync else None
+
+    def barrier_forward(self) -> None:
+        if not self.inkernel_sync:
+            self.mu_hdl.barrier(channel=0)
+
+    def barrier_backward(self) -> None:
+        if not self.inkernel_sync:
+            self.scratch_hdl.barrier(channel=0)
 
     # -- buffer rotation ---------------------------------------------------------------------------
     def next_forward(self) -> int:
@@ -106,12 +131,12 @@ class _PeerKLLoss(torch.autograd.Function):
         k = exch.next_forward()
         with torch.cuda.device(z.device):
             exch.mu_sym[k].copy_(mu.detach())                       # publish this rank's rows
-            exch.mu_hdl.barrier(channel=0)                          # every rank's rows are visible after this point of the stream
+            exch.barrier_forward()                                  # host-side barrier mode only; else the prologue kernel waits itself
             st = lib.tcelbo_klloss_forward_peer(z.data_ptr(), z.stride(0), mu.data_ptr(), mu.stride(0),
                                                 exch.mu_tables[k].data_ptr(), d, logvar.data_ptr(), logvar.stride(0),
                                                 b_loc, exch.world, exch.rank, d, dataset_size, flags, beta,
                                                 out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
-                                                None, ws.data_ptr(), nbytes, _stream(z))
+                                                None, exch.sync_arg(), ws.data_ptr(), nbytes, _stream(z))
         _lib.check(st, "tcelbo_klloss_forward_peer")
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(z, mu, logvar, ws)
@@ -147,11 +172,11 @@ class _PeerKLLoss(torch.autograd.Function):
                 g_loss.data_ptr(), *(t.data_ptr() if t is not None else None for t in opt),
                 grad_z.data_ptr(), d, grad_mu.data_ptr(), d, grad_lv.data_ptr(), d,
                 ws.data_ptr(), ws.numel(), scratch.data_ptr(), exch.scratch_bytes,
-                exch.scratch_tables[k].data_ptr(), None, _stream(z))
+                exch.scratch_tables[k].data_ptr(), None, exch.sync_arg(), _stream(z))
 
         with torch.cuda.device(z.device):
             _lib.check(call(_lib.PEER_SWEEP), "tcelbo_klloss_backward_peer(sweep)")
-            exch.scratch_hdl.barrier(channel=0)                     # every rank's column sums are complete and visible
+            exch.barrier_backward()                                 # host-side barrier mode only; else the finalize kernel waits itself
             _lib.check(call(_lib.PEER_FINISH), "tcelbo_klloss_backward_peer(finish)")
         return grad_z, grad_mu, grad_lv, None, None, None, None
 

@@ -16,10 +16,19 @@ from .. import ops
 from .. import utils as _utils
 
 
-def _singleton_writer():
-    """The process-wide writer holder the training driver updates: the reference's ``utils.SingletonWriter`` after
-    :func:`intro_tc_vae_b200.install` (train.py:100-103,212 set ``writer`` / ``cur_iter`` on it), this package's otherwise."""
-    return _utils.SingletonWriter()
+class _WriterView:
+    """``writer`` / ``cur_iter`` of the process-wide holder; the reference's class has no defaults (train.py:100-103,212 assign
+    them before the first step), so a holder nobody has set up yet reads as "no writer, iteration 0"."""
+
+    def __init__(self, holder):
+        self.writer = getattr(holder, "writer", None)
+        self.cur_iter = getattr(holder, "cur_iter", 0)
+
+
+def _singleton_writer() -> _WriterView:
+    """The writer holder the training driver updates: the reference's ``utils.SingletonWriter`` after
+    :func:`intro_tc_vae_b200.install`, this package's otherwise."""
+    return _WriterView(_utils.SingletonWriter())
 
 
 class TCLossMixin:

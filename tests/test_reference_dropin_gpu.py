@@ -18,6 +18,15 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), re
 N_DATA = 16704
 
 
+@pytest.fixture(autouse=True)
+def _restore_package_writer():
+    """install() aliases the package's SingletonWriter to the reference's; undo that so later tests see the package's own."""
+    from intro_tc_vae_b200 import utils as fast_utils
+    saved = fast_utils.SingletonWriter
+    yield
+    fast_utils.SingletonWriter = saved
+
+
 class _Dataset:
     def __len__(self):
         return N_DATA

@@ -569,7 +569,7 @@ def test_peer_exchange_entry_points_emulated_on_one_gpu(B, D, parts, family):
     zs, lvs = [z[s].contiguous() for s in shards], [lv[s].contiguous() for s in shards]
     for r in range(parts):
         _lib.check(lib.tcelbo_klloss_forward_peer(P(zs[r]), D, P(mu_parts[r]), D, P(mu_table), D, P(lvs[r]), D, b_loc, parts, r, D, N,
-                                                  flags, beta, *[P(t) for t in rows[r]], None, P(ws[r]), ws_bytes, st), "forward_peer")
+                                                  flags, beta, *[P(t) for t in rows[r]], None, None, P(ws[r]), ws_bytes, st), "forward_peer")
     for k in range(4):
         assert relerr(torch.cat([rows[r][k] for r in range(parts)]), outs_r[k]) < 2e-6
     gs = [[w[s].contiguous() for w in g] for s in shards]
@@ -580,16 +580,16 @@ def test_peer_exchange_entry_points_emulated_on_one_gpu(B, D, parts, family):
         for r in range(parts):
             _lib.check(lib.tcelbo_klloss_backward_peer(phase, P(zs[r]), D, P(mu_parts[r]), D, P(lvs[r]), D, b_loc, parts, r, D, N, flags,
                                                        beta, *[P(t) for t in gs[r]], P(gz[r]), D, P(gmu[r]), D, P(glv[r]), D,
-                                                       P(ws[r]), ws_bytes, P(scratch[r]), sc_bytes, P(sc_table), None, st), "backward_peer")
+                                                       P(ws[r]), ws_bytes, P(scratch[r]), sc_bytes, P(sc_table), None, None, st), "backward_peer")
     assert relerr(torch.cat(gz), z_r.grad) < 1e-5
     assert relerr(torch.cat(glv), lv_r.grad) < 1e-5
     assert relerr(torch.cat(gmu), mu_r.grad) < 1e-5
     # argument validation
     assert lib.tcelbo_klloss_backward_peer(3, P(zs[0]), D, P(mu_parts[0]), D, P(lvs[0]), D, b_loc, parts, 0, D, N, flags, beta,
                                            *[P(t) for t in gs[0]], P(gz[0]), D, P(gmu[0]), D, P(glv[0]), D, P(ws[0]), ws_bytes,
-                                           P(scratch[0]), sc_bytes, P(sc_table), None, st) != 0
+                                           P(scratch[0]), sc_bytes, P(sc_table), None, None, st) != 0
     assert lib.tcelbo_klloss_forward_peer(P(zs[0]), D, P(mu_parts[0]), D, P(mu_table), D, P(lvs[0]), D, b_loc, parts, parts, D, N,
-                                          flags, beta, *[P(t) for t in rows[0]], None, P(ws[0]), ws_bytes, st) != 0
+                                          flags, beta, *[P(t) for t in rows[0]], None, None, P(ws[0]), ws_bytes, st) != 0
 
 
 def test_two_gpu_sharded_equals_single_when_available():
