@@ -509,7 +509,8 @@ def run_ours(args):
                        "l2": "flushed between timed steps by writing a 256 MiB buffer (outside the event pairs)",
                        "launch": graph_note,
                        "exchange": {"none": "none (one GPU)", "nccl": "NCCL all-gather + reduce-scatter",
-                                    "peer": "library kernels over NVLink peer memory (symmetric memory + 2 barriers)"}[exchange_note]},
+                                    "peer": "library kernels over NVLink peer memory (gather / reduce-scatter inside the prologue / finalize kernels, "
+                                            "in-kernel flag barriers over symmetric memory)"}[exchange_note]},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 3 * b_loc * D * 4, "d2h_bytes_per_step": 2 * b_loc * D * 4 + 4},
             "dropin": {"what": "same step through the reference's signatures: ops.reparameterize -> TCLossMixin.compute_kl_loss(z, mu, logvar) "

@@ -182,11 +182,17 @@ int tcelbo_klloss_backward_ex(const float* z, int64_t ldz, const float* mu_all, 
  * issue the same sequence of peer calls; a rank that never arrives makes the others trap after ~2 s.
  *   flag_parts  DEVICE table of n_ranks pointers; entry r = rank r's flag array of 2*n_ranks 32-bit words, zero-initialised
  *               once (before the first call, with a real barrier after the zeroing), mapped into every process
- *   state       DEVICE, local to this rank: 4 zero-initialised 32-bit words (barrier epochs and CTA tickets) */
+ *   state       DEVICE, local to this rank: 4 zero-initialised 32-bit words (the barrier counters of the two exchanges)
+ * The counters are advanced by the kernel BEFORE the waiting one on the stream: tcelbo_peer_publish (which also copies this
+ * rank's rows of mu into its mapped buffer) for the forward exchange -- call it instead of a plain copy -- and the backward
+ * prologue (TCELBO_PEER_SWEEP) for the backward exchange. */
 typedef struct tcelbo_peer_sync {
     unsigned int* const* flag_parts;
     unsigned int* state;
 } tcelbo_peer_sync;
+
+int tcelbo_peer_publish(const float* mu_loc, int64_t ldmu, int b_loc, int d, float* published /* [b_loc, d] dense, mapped */,
+                        const tcelbo_peer_sync* sync, void* stream);
 
 #define TCELBO_PEER_SWEEP  1
 #define TCELBO_PEER_FINISH 2

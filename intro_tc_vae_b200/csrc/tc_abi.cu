@@ -263,6 +263,7 @@ static int backward_impl(const float* z, int64_t ldz, const float* mu_all, int64
     up.g_log_qz = g_log_qz; up.g_log_qz_prod = g_log_qz_prod; up.g_loss = lf.g_loss; up.g_kl = lf.g_kl;
     up.g_loss_mean = lf.fz.g_loss_mean; up.g_kl_mean = lf.fz.g_kl_mean; up.g_expelbo = lf.fz.g_expelbo; up.e_rows = lf.fz.e_rows;
     up.scale = lf.fz.scale; up.g_rec_rows = lf.fz.g_rec_rows; up.beta = lf.beta;
+    up.epoch = (peers.on() && peers.sync.on()) ? peers.sync.state + 1 : nullptr;
     if ((peers.phase & 1) && (e = launch_bwd_prep(p, up, S, gps, gj, lf.on ? gk : nullptr, Gpart, zero_n, st)) != cudaSuccess)
         return fail_cuda(e, "bwd_prep");
 
@@ -377,6 +378,13 @@ int tcelbo_klloss_forward_peer(const float* z, int64_t ldz, const float* mu_loc,
     if (sync) peers.sync = PeerSync{sync->flag_parts, sync->state, 0, rank, n_ranks};
     return forward_impl(z, ldz, mu_loc, ldmu, logvar, ldlv, b_loc, b_loc * n_ranks, rank * b_loc, d, dataset_size, flags,
                         log_qz, log_qz_prod, lf, workspace, workspace_bytes, stream, peers);
+}
+
+int tcelbo_peer_publish(const float* mu_loc, int64_t ldmu, int b_loc, int d, float* published, const tcelbo_peer_sync* sync, void* stream) {
+    if (!mu_loc || !published || b_loc < 1 || d < 1 || ldmu < d) return fail(TCELBO_ERR_INVALID, "bad argument");
+    if (sync && !sync->state) return fail(TCELBO_ERR_INVALID, "peer_sync needs the state words");
+    cudaError_t e = launch_publish(mu_loc, ldmu, b_loc, d, published, sync ? sync->state : nullptr, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? TCELBO_OK : fail_cuda(e, "publish");
 }
 
 int tcelbo_klloss_backward_peer(int phase, const float* z, int64_t ldz, const float* mu_loc, int64_t ldmu, const float* logvar, int64_t ldlv,

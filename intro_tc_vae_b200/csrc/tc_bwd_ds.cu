@@ -449,7 +449,6 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
             a.grad_mu[(int64_t)j * a.ldgmu + dd] = g;
         }
     }
-    if (a.scratch_parts != nullptr && a.sync.on()) peer_barrier_done(a.sync);
 }
 
 // variant 0 is the shipped configuration; the others are tuning points kept for tools/tune_bwd.py (profiles/r2_bwd_ds_sweep.md)

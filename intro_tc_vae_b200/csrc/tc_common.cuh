@@ -119,23 +119,24 @@ __device__ __forceinline__ void weight_of(const Weights& w, int i_glob, int j, f
 }
 
 // ---- cross-rank barrier inside a kernel, over peer-mapped flags (one process per GPU, NVLink) --------------------
-// Rank r owns a flag array of n_channels * n_ranks words in memory every rank has mapped.  Barrier number e+1 of a channel:
-// every rank stores e+1 into slot [channel][its rank] of EVERY rank's array (release, system scope) and then waits until all
-// n_ranks slots of its own array have reached e+1 (acquire).  `epoch` (local) counts the barriers this rank has completed on
-// the channel; it is advanced by the last CTA of the kernel to leave, so every CTA of one launch reads the same value.
+// Rank r owns a flag array of n_channels * n_ranks words in memory every rank has mapped.  Barrier number e of a channel:
+// every rank stores e into slot [channel][its rank] of EVERY rank's array (release, system scope) and then waits until all
+// n_ranks slots of its own array have reached e (acquire).  The barrier number is `state[channel]`, a local counter that the
+// PREVIOUS kernel of the stream has already advanced (the publish kernel for the forward exchange, the backward prologue
+// for the backward exchange), so every CTA of the waiting kernel reads the same, stable value and no ticket is needed.
 // Kernels that use this must be launched by all ranks in the same order; a rank that never arrives traps the others after
 // ~2 s instead of hanging the GPUs.
 struct PeerSync {
     unsigned int* const* flag_parts;   // device table [n_ranks] of the ranks' flag arrays (nullptr: no in-kernel barrier)
-    unsigned int* state;               // local, zero-initialised: [2*channel] = epoch, [2*channel+1] = CTA ticket
+    unsigned int* state;               // local, zero-initialised: [channel] = number of the current barrier
     int channel, rank, n_ranks;
-    __device__ __forceinline__ bool on() const { return flag_parts != nullptr; }
+    __host__ __device__ __forceinline__ bool on() const { return flag_parts != nullptr; }
 };
 
-// one CTA signals (first n_ranks threads), every CTA waits; call with all threads of the CTA
+// CTA 0 signals (its first n_ranks threads), every CTA waits; call with all threads of the CTA
 __device__ __forceinline__ void peer_barrier(const PeerSync& ps) {
-    const unsigned int want = *reinterpret_cast<volatile unsigned int*>(ps.state + 2 * ps.channel) + 1u;
     if ((int)threadIdx.x < ps.n_ranks) {
+        const unsigned int want = *reinterpret_cast<volatile unsigned int*>(ps.state + ps.channel);
         if (blockIdx.x == 0) {
             unsigned int* dst = ps.flag_parts[threadIdx.x] + ps.channel * ps.n_ranks + ps.rank;
             asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(dst), "r"(want) : "memory");
@@ -149,19 +150,6 @@ __device__ __forceinline__ void peer_barrier(const PeerSync& ps) {
         } while ((int)(v - want) < 0);
     }
     __syncthreads();
-}
-
-// at the very end of the kernel, all threads: the last CTA to leave publishes the new epoch and resets the ticket
-__device__ __forceinline__ void peer_barrier_done(const PeerSync& ps) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(ps.state + 2 * ps.channel + 1, 1u) == gridDim.x - 1) {
-            ps.state[2 * ps.channel + 1] = 0u;
-            __threadfence();
-            atomicAdd(ps.state + 2 * ps.channel, 1u);
-        }
-    }
 }
 
 // online logsumexp in base 2: (m, s) <- (m, s) (+) 2^x

@@ -19,6 +19,15 @@ namespace tcelbo {
 // =====================================================================================================
 // Prologues: pad/copy the column operand, derive the per-(i,d) constants
 // =====================================================================================================
+// Peer exchange, forward: copy this rank's rows of mu into its peer-mapped buffer and open the next forward barrier
+// (the prologue kernel that follows on the stream signals and waits on that number, tc_common.cuh: PeerSync).
+__global__ void publish_kernel(const float* __restrict__ src, int64_t ld, int b_loc, int d, float* __restrict__ dst, unsigned int* epoch) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && epoch != nullptr) atomicAdd(epoch, 1u);
+    const int64_t n = (int64_t)b_loc * d;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x)
+        dst[idx] = src[(idx / d) * ld + idx % d];
+}
+
 template <bool kParts>
 __global__ void prep_kernel(const PrepArgs a) {
     const int64_t n_col = (int64_t)a.bg_pad * a.dp, n_row = (int64_t)a.bl_pad * a.dp;
@@ -66,7 +75,6 @@ __global__ void prep_kernel(const PrepArgs a) {
         }
         a.mu_pad[idx] = v;
     }
-    if (kParts && a.sync.on()) peer_barrier_done(a.sync);
 }
 
 // =====================================================================================================
@@ -380,6 +388,7 @@ __global__ void bwd_prep_kernel(const BwdUpstream u, const float* __restrict__ S
     const float gl_mean = u.g_loss_mean ? u.g_loss_mean[0] * inv_b : 0.0f;
     const float gk_mean = u.g_kl_mean ? u.g_kl_mean[0] * inv_b : 0.0f;
     const float ge = u.g_expelbo ? u.g_expelbo[0] * (-2.0f * u.scale * inv_b) : 0.0f;
+    if (u.epoch != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(u.epoch, 1u);   // opens the backward exchange's barrier
     auto g_loss_of = [&](int i, float& g_rec) {                 // dLoss/dloss_rows[i]; g_rec = its exp-ELBO part (= dLoss/drec_rows[i])
         g_rec = u.g_expelbo ? ge * u.e_rows[i] : 0.0f;
         return (u.g_loss ? u.g_loss[i] : 0.0f) + gl_mean + g_rec;
@@ -437,6 +446,12 @@ static cudaError_t launch_fwd_t(const Plan& p, const FwdArgs& a, cudaStream_t st
     }
     LaunchScope scope(kKernFwd, st);
     tc_fwd_kernel<LPR, JTS><<<p.seg_fwd.n_ctas, kFwdWarps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_publish(const float* src, int64_t ld, int b_loc, int d, float* dst, unsigned int* epoch, cudaStream_t st) {
+    LaunchScope scope(kKernNone, st);
+    publish_kernel<<<grid_for((int64_t)b_loc * d, 256, 148 * 4), 256, 0, st>>>(src, ld, b_loc, d, dst, epoch);
     return cudaGetLastError();
 }
 

@@ -82,6 +82,7 @@ struct BwdFinArgs {
 };
 
 cudaError_t launch_prep(const PrepArgs& a, cudaStream_t st);
+cudaError_t launch_publish(const float* src, int64_t ld, int b_loc, int d, float* dst, unsigned int* epoch, cudaStream_t st);
 cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st);
 cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st);
 // Upstream gradients of the backward prologue.  Per row i (any pointer may be null):
@@ -94,6 +95,7 @@ struct BwdUpstream {
     const float* g_loss_mean; const float* g_kl_mean; const float* g_expelbo; const float* e_rows; float scale;
     float* g_rec_rows;
     float beta;
+    unsigned int* epoch;          // peer exchange with in-kernel barriers: the backward barrier counter this prologue advances
 };
 cudaError_t launch_bwd_prep(const Plan& p, const BwdUpstream& u, const float* S, float* gps, float* gj, float* gk,
                             float* zero, size_t zero_n, cudaStream_t st);

@@ -179,8 +179,7 @@ class GraphedKLLoss:
             # peer-memory exchange: the library's prologue / finalize kernels gather mu and reduce-scatter its gradient over NVLink;
             # reparameterize and the batch mean are fused here too (publish copy, barrier, 3 + barrier + 3 launches)
             k = exch.next_forward()
-            exch.mu_sym[k].copy_(mu)
-            exch.barrier_forward()
+            exch.publish(mu, k)
             fz = _lib.Fusion(eps=P(eps), ldeps=d, z_out=P(z), ldz_out=d, loss_mean=P(self._loss))
             _lib.check(lib.tcelbo_klloss_forward_peer(None, 0, P(mu), d, P(exch.mu_tables[k]), d, P(lv), d, b_loc, self.world,
                                                       self.rank, d, n, flags, beta, *rows, ctypes.byref(fz), exch.sync_arg(), P(self._ws), self._ws.numel(), st),

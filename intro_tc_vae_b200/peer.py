@@ -85,8 +85,16 @@ class PeerExchange:
         import ctypes
         return ctypes.byref(self._sync_args) if self.inkernel_sync else None
 
-    def barrier_forward(self) -> None:
-        if not self.inkernel_sync:
+    def publish(self, mu: Tensor, k: int) -> None:
+        """Make this rank's rows visible to the other ranks (buffer k) and order the gather after everybody's publish: with in-kernel
+        barriers one library kernel copies the rows and opens the barrier the prologue kernel waits on; otherwise a copy + a
+        symmetric-memory barrier on the stream."""
+        if self.inkernel_sync:
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(_lib.load().tcelbo_peer_publish(mu.data_ptr(), mu.stride(0), self.b_loc, self.d, self.mu_sym[k].data_ptr(),
+                                                       self.sync_arg(), st), "tcelbo_peer_publish")
+        else:
+            self.mu_sym[k].copy_(mu)
             self.mu_hdl.barrier(channel=0)
 
     def barrier_backward(self) -> None:
@@ -130,8 +138,7 @@ class _PeerKLLoss(torch.autograd.Function):
         out = [torch.empty(b_loc, dtype=torch.float32, device=z.device) for _ in range(4)]
         k = exch.next_forward()
         with torch.cuda.device(z.device):
-            exch.mu_sym[k].copy_(mu.detach())                       # publish this rank's rows
-            exch.barrier_forward()                                  # host-side barrier mode only; else the prologue kernel waits itself
+            exch.publish(mu.detach(), k)                            # this rank's rows -> its mapped buffer (+ barrier)
             st = lib.tcelbo_klloss_forward_peer(z.data_ptr(), z.stride(0), mu.data_ptr(), mu.stride(0),
                                                 exch.mu_tables[k].data_ptr(), d, logvar.data_ptr(), logvar.stride(0),
                                                 b_loc, exch.world, exch.rank, d, dataset_size, flags, beta,
