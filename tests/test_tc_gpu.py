@@ -606,3 +606,60 @@ def test_two_gpu_sharded_equals_single_when_available():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MISMATCH" not in out.stdout
+
+
+@pytest.mark.parametrize("B,D,parts", [(256, 128, 2), (384, 64, 4)])
+def test_peer_entry_points_with_fused_prologue_and_epilogue_emulated(B, D, parts):
+    """The peer-memory entry points with tcelbo_fusion (what GraphedKLLoss replays on N > 1 GPUs: reparameterize in the prologue,
+    batch mean in the finalize, chain rule through z in the backward finalize), P ranks played one after the other on one GPU
+    (sync = NULL: the in-kernel barriers need the ranks to run concurrently), against the single-GPU direct step."""
+    import ctypes
+    from intro_tc_vae_b200 import _lib
+    from intro_tc_vae_b200.graphs import GraphedKLLoss
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    N, beta = 16704, 0.5
+    mu_c, lv_c, eps_c = _random_latents(B, D, "base", seed=91)
+    mu, lv, eps = mu_c.to(dev), lv_c.to(dev), eps_c.to(dev)
+    ref = GraphedKLLoss(B, D, N, beta, dev, capture=False)
+    loss_ref, dmu_ref, dlv_ref = [t.clone() for t in ref(mu, lv, eps)]
+
+    b_loc = B // parts
+    flags = _lib.EST_MSS | _lib.VAR_ROW | _lib.SAVE_FOR_BACKWARD
+    ws_bytes = lib.tcelbo_workspace_bytes(b_loc, B, D, flags)
+    sc_bytes = lib.tcelbo_backward_scratch_bytes(b_loc, B, D, flags)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    P = lambda t: t.data_ptr()                                       # noqa: E731
+    shards = [slice(r * b_loc, (r + 1) * b_loc) for r in range(parts)]
+    mus, lvs, epss = ([t[s].contiguous() for s in shards] for t in (mu, lv, eps))
+    pub = [torch.empty(b_loc, D, device=dev) for _ in range(parts)]
+    for r in range(parts):                                           # tcelbo_peer_publish without a sync struct is a plain strided copy
+        _lib.check(lib.tcelbo_peer_publish(P(mus[r]), D, b_loc, D, P(pub[r]), None, st), "publish")
+    mu_table = torch.tensor([P(t) for t in pub], dtype=torch.int64, device=dev)
+    ws = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in range(parts)]
+    scratch = [torch.empty(sc_bytes, dtype=torch.uint8, device=dev) for _ in range(parts)]
+    sc_table = torch.tensor([P(t) for t in scratch], dtype=torch.int64, device=dev)
+    rows = [[torch.empty(b_loc, device=dev) for _ in range(4)] for _ in range(parts)]
+    zs = [torch.empty(b_loc, D, device=dev) for _ in range(parts)]
+    means = [torch.empty((), device=dev) for _ in range(parts)]
+    one = torch.ones((), device=dev)
+    for r in range(parts):
+        fz = _lib.Fusion(eps=P(epss[r]), ldeps=D, z_out=P(zs[r]), ldz_out=D, loss_mean=P(means[r]))
+        _lib.check(lib.tcelbo_klloss_forward_peer(None, 0, P(mus[r]), D, P(mu_table), D, P(lvs[r]), D, b_loc, parts, r, D, N, flags, beta,
+                                                  *[P(t) for t in rows[r]], ctypes.byref(fz), None, P(ws[r]), ws_bytes, st), "forward_peer")
+    loss = torch.stack(means).mean()                                 # mean of the per-rank means == global mean (equal shards)
+    assert relerr(loss.reshape(1), loss_ref.reshape(1)) < 2e-6
+    assert relerr(torch.cat(zs), ref._z) < 1e-6
+    gz = [torch.empty(b_loc, D, device=dev) for _ in range(parts)]
+    gmu = [torch.empty(b_loc, D, device=dev) for _ in range(parts)]
+    glv = [torch.empty(b_loc, D, device=dev) for _ in range(parts)]
+    for phase in (_lib.PEER_SWEEP, _lib.PEER_FINISH):
+        for r in range(parts):
+            fb = _lib.Fusion(eps=P(epss[r]), ldeps=D, g_loss_mean=P(one))
+            _lib.check(lib.tcelbo_klloss_backward_peer(phase, None, 0, P(mus[r]), D, P(lvs[r]), D, b_loc, parts, r, D, N, flags, beta,
+                                                       None, None, None, None, P(gz[r]), D, P(gmu[r]), D, P(glv[r]), D,
+                                                       P(ws[r]), ws_bytes, P(scratch[r]), sc_bytes, P(sc_table), ctypes.byref(fb), None, st),
+                       "backward_peer")
+    # every rank differentiated ITS mean over b_loc rows: the global-mean gradient is 1/parts of the concatenation
+    assert relerr(torch.cat(gmu) / parts, dmu_ref) < 1e-5
+    assert relerr(torch.cat(glv) / parts, dlv_ref) < 1e-5
