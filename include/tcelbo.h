@@ -179,7 +179,7 @@ int tcelbo_klloss_backward_ex(const float* z, int64_t ldz, const float* mu_all, 
  * tcelbo_klloss_forward_peer and before the TCELBO_PEER_FINISH call, as described above).  With it, the prologue kernel signals
  * "my rows are published" to every rank and waits for all ranks before it gathers (its row work overlaps the wait), and the
  * finalize kernel does the same for "my sweep is done" before it reduces: no barrier launches at all.  Every rank must then
- * issue the same sequence of peer calls; a rank that never arrives makes the others trap after ~2 s.
+ * issue the same sequence of peer calls; a rank that never arrives makes the others trap after ~30 s.
  *   flag_parts  DEVICE table of n_ranks pointers; entry r = rank r's flag array of 2*n_ranks 32-bit words, zero-initialised
  *               once (before the first call, with a real barrier after the zeroing), mapped into every process
  *   state       DEVICE, local to this rank: 4 zero-initialised 32-bit words (the barrier counters of the two exchanges)

@@ -363,7 +363,7 @@ static cudaError_t launch_bwd_ds_t(const Plan& p, const BwdFusedArgs& u, BwdFinA
     const int n_rb = (p.bl_pad + ROWS - 1) / ROWS;
     const int n_slices = p.dp / DPS;
     const int T = p.bg_pad / JT;
-    const Segments seg = plan_segments((int64_t)n_rb * n_slices, T, p.sms * ctas_per_sm, g_ds_seg_target > 0 ? g_ds_seg_target : 1024 / JT);
+    const Segments seg = plan_segments((int64_t)n_rb * n_slices, T, p.sms * ctas_per_sm, g_ds_seg_target > 0 ? g_ds_seg_target : 2048 / JT);     // 128 tiles of 16 columns per CTA (profiles/r2_notes.md)
     fin->seg = seg; fin->tiles_per_block = T; fin->n_rb = n_rb; fin->rows_per_block = ROWS; fin->slice_dp = DPS;
     if (u.plan_only) return cudaSuccess;
     BwdDsArgs a;

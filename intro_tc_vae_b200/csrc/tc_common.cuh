@@ -125,7 +125,7 @@ __device__ __forceinline__ void weight_of(const Weights& w, int i_glob, int j, f
 // PREVIOUS kernel of the stream has already advanced (the publish kernel for the forward exchange, the backward prologue
 // for the backward exchange), so every CTA of the waiting kernel reads the same, stable value and no ticket is needed.
 // Kernels that use this must be launched by all ranks in the same order; a rank that never arrives traps the others after
-// ~2 s instead of hanging the GPUs.
+// ~30 s instead of hanging the GPUs.
 struct PeerSync {
     unsigned int* const* flag_parts;   // device table [n_ranks] of the ranks' flag arrays (nullptr: no in-kernel barrier)
     unsigned int* state;               // local, zero-initialised: [channel] = number of the current barrier
@@ -146,7 +146,7 @@ __device__ __forceinline__ void peer_barrier(const PeerSync& ps) {
         unsigned int v;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-            if ((int)(v - want) < 0 && clock64() - t0 > 4000000000ll) __trap();
+            if ((int)(v - want) < 0 && clock64() - t0 > 60000000000ll) __trap();     // ~30 s: ranks may start seconds apart
         } while ((int)(v - want) < 0);
     }
     __syncthreads();

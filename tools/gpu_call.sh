@@ -1,21 +1,6 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-for N in 8 4; do
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2l_bench_n$N.json 2> gpurun_out/r2l_bench_n$N.err
-tail -2 gpurun_out/r2l_bench_n$N.err
-python -c "
-import json;j=json.loads([l for l in open('gpurun_out/r2l_bench_n$N.json') if l.startswith('{')][-1])
-print($N, {k:j[k] for k in ('ms_per_step','value','gpu_launches')}, j['e2e']['ms_per_step'], j['dropin']['ms_per_step'], j['e2e_dropin']['ms_per_step'], j['roofline']['kernel_ms'], (j['train'] or {}).get('value'))
-"
-done
-TCELBO_PEER_SYNC=host timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 8 --steps 20 --warmup 5 --no-train > gpurun_out/r2l_bench_n8_hostsync.json 2> gpurun_out/r2l_bench_n8_hostsync.err
-python -c "
-import json;j=json.loads([l for l in open('gpurun_out/r2l_bench_n8_hostsync.json') if l.startswith('{')][-1])
-print('hostsync', {k:j[k] for k in ('ms_per_step','value')}, j['e2e']['ms_per_step'], j['dropin']['ms_per_step'], j['e2e_dropin']['ms_per_step'])
-"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 10 --warmup 3 --batch 32768 --zdim 512 --no-train > gpurun_out/r2l_bench_cfg4_n8.json 2> gpurun_out/r2l_bench_cfg4_n8.err
-python -c "
-import json;j=json.loads([l for l in open('gpurun_out/r2l_bench_cfg4_n8.json') if l.startswith('{')][-1])
-print('cfg4', {k:j[k] for k in ('ms_per_step','value')}, j['e2e']['ms_per_step'], j['roofline']['kernel_ms'])
-"
+timeout 300 python tools/tune_bwd.py --variants=0 --reps 2 --rows 1024 > gpurun_out/r2n_plain.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'tc_fwd_kernel|tc_bwd_ds_kernel|prep_kernel|finalize' --launch-skip 7 --launch-count 7 -o gpurun_out/r2n_rows1024 python tools/tune_bwd.py --variants=0 --reps 2 --rows 1024 > gpurun_out/r2n_ncu.log 2>&1
+tail -3 gpurun_out/r2n_ncu.log
