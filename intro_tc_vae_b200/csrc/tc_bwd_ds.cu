@@ -451,6 +451,100 @@ __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
     }
 }
 
+__device__ __forceinline__ float4 ld_volatile_f4(const void* p) {                 // peer-mapped memory: no L1 / nc path
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+// The same finalize with 16-byte accesses (4 dims per thread): launched when d % 4 == 0 and every caller-side pitch / pointer is
+// 16-byte aligned; bwd_fused_finalize_kernel covers the rest.  At one rank of eight the step spends as long in its small kernels
+// as in 5 % of its sweeps, so their memory-level parallelism matters there.
+__global__ void bwd_fused_finalize_v4_kernel(const BwdFinArgs a) {
+    const int d4 = a.d / 4;
+    const int64_t n_row = (int64_t)a.b_loc * d4;
+    const int64_t n_col = a.scratch_parts != nullptr ? 0 : (int64_t)a.b_glob * d4;
+    const size_t split_stride = (size_t)a.bl_pad * a.dp;
+    const bool rows_own_mu = a.scratch_parts != nullptr || a.eps != nullptr;
+    if (a.scratch_parts != nullptr && a.sync.on()) peer_barrier(a.sync);
+    auto ld4 = [](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_row + n_col; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (idx < n_row) {
+            const int i = (int)(idx / d4), dd = 4 * (int)(idx % d4);
+            const size_t o = (size_t)i * a.dp + dd;
+            float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sc = sa;
+            const int64_t qb = (int64_t)(dd / a.slice_dp) * a.n_rb + i / a.rows_per_block;
+            const int n_slots = seg_slots(a.seg, qb, a.tiles_per_block);
+            for (int s0 = 0; s0 < n_slots; s0 += 4) {
+                float4 va[4], vc[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool ok = s0 + k < n_slots;
+                    va[k] = ok ? ld4(a.Apart + (size_t)(s0 + k) * split_stride + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    vc[k] = ok ? ld4(a.CRpart + (size_t)(s0 + k) * split_stride + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { sa = f4_add(sa, va[k]); sc = f4_add(sc, vc[k]); }
+            }
+            const float4 vr = ld4(a.vr + o), ns = ld4(a.ns + o);
+            float glv[4] = {vr.x * (kTwoLn2 * sc.x), vr.y * (kTwoLn2 * sc.y), vr.z * (kTwoLn2 * sc.z), vr.w * (kTwoLn2 * sc.w)};
+            const float gz[4] = {kTwoLn2 * ns.x * sa.x, kTwoLn2 * ns.y * sa.y, kTwoLn2 * ns.z * sa.z, kTwoLn2 * ns.w * sa.w};
+            float lv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (a.gk != nullptr || a.eps != nullptr) {
+                const float4 l4 = *reinterpret_cast<const float4*>(a.lv + (int64_t)i * a.ldlv + dd);
+                lv[0] = l4.x; lv[1] = l4.y; lv[2] = l4.z; lv[3] = l4.w;
+            }
+            if (a.gk != nullptr) {
+                const float gk = a.gk[i];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) glv[e] += gk * 0.5f * (expf(lv[e]) - 1.0f);
+            }
+            if (a.eps != nullptr) {                                                  // through z = mu + eps*std
+                const float4 e4 = *reinterpret_cast<const float4*>(a.eps + (int64_t)i * a.ldeps + dd);
+                const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) glv[e] += gz[e] * ev[e] * (0.5f * expf(0.5f * lv[e]));
+            }
+            *reinterpret_cast<float4*>(a.grad_z + (int64_t)i * a.ldgz + dd) = make_float4(gz[0], gz[1], gz[2], gz[3]);
+            *reinterpret_cast<float4*>(a.grad_lv + (int64_t)i * a.ldglv + dd) = make_float4(glv[0], glv[1], glv[2], glv[3]);
+            if (rows_own_mu) {
+                const size_t og = (size_t)(a.row_offset + i) * a.dp + dd;
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.scratch_parts != nullptr) {
+                    // reduce-scatter of the column gradient as this kernel's load phase: 16-byte loads of the local rows of every rank's accumulator
+                    for (int p0 = 0; p0 < a.n_ranks; p0 += 8) {
+                        float4 v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            v[k] = (p0 + k < a.n_ranks) ? ld_volatile_f4(static_cast<const char*>(a.scratch_parts[p0 + k]) + a.g_off + og * sizeof(float))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) g = f4_add(g, v[k]);
+                    }
+                } else {
+                    g = ld4(a.Gpart + og);
+                }
+                g = f4_scale(g, -kTwoLn2);
+                const int64_t mrow = a.scratch_parts != nullptr ? i : a.row_offset + i;      // mu_all = this rank's rows only in the peer mode
+                if (a.gk != nullptr) g = f4_add(g, f4_scale(*reinterpret_cast<const float4*>(a.mu_all + mrow * a.ldmu + dd), a.gk[i]));
+                if (a.eps != nullptr) g = f4_add(g, make_float4(gz[0], gz[1], gz[2], gz[3]));
+                *reinterpret_cast<float4*>(a.grad_mu + mrow * a.ldgmu + dd) = g;              // grad_mu covers the local rows only in the peer mode
+            }
+        } else {
+            const int64_t k = idx - n_row;
+            const int j = (int)(k / d4), dd = 4 * (int)(k % d4);
+            const int i = j - a.row_offset;
+            const bool local = i >= 0 && i < a.b_loc;
+            if (local && rows_own_mu) continue;
+            float4 g = f4_scale(ld4(a.Gpart + (size_t)j * a.dp + dd), -kTwoLn2);
+            if (a.gk != nullptr && local) g = f4_add(g, f4_scale(*reinterpret_cast<const float4*>(a.mu_all + (int64_t)j * a.ldmu + dd), a.gk[i]));
+            *reinterpret_cast<float4*>(a.grad_mu + (int64_t)j * a.ldgmu + dd) = g;
+        }
+    }
+}
+
 // variant 0 is the shipped configuration; the others are tuning points kept for tools/tune_bwd.py (profiles/r2_bwd_ds_sweep.md)
 static cudaError_t launch_bwd_ds(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* fin, int variant, cudaStream_t st) {
     if (p.small) {                       // B = 3 / 64-sized batches: 4 rows per warp so that row blocks x tiles covers more SMs
@@ -488,10 +582,14 @@ cudaError_t launch_bwd_fused(const Plan& p, const BwdFusedArgs& a, BwdFinArgs* f
 }
 
 cudaError_t launch_bwd_fused_finalize(const Plan& p, const BwdFinArgs& a, cudaStream_t st) {
-    const int64_t n = (int64_t)p.b_loc * p.d + (int64_t)p.b_glob * p.d;
+    auto ok16 = [](const void* ptr, int64_t ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && ld % 4 == 0); };
+    const bool vec = p.d % 4 == 0 && ok16(a.grad_z, a.ldgz) && ok16(a.grad_lv, a.ldglv) && ok16(a.grad_mu, a.ldgmu) && ok16(a.mu_all, a.ldmu)
+                     && ok16(a.lv, a.ldlv) && ok16(a.eps, a.ldeps) && (a.g_off % 16 == 0);
+    const int64_t n = ((int64_t)p.b_loc * p.d + (int64_t)p.b_glob * p.d) / (vec ? 4 : 1);
     int64_t g = (n + 255) / 256; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1;
     LaunchScope scope(kKernNone, st);
-    bwd_fused_finalize_kernel<<<(int)g, 256, 0, st>>>(a);
+    if (vec) bwd_fused_finalize_v4_kernel<<<(int)g, 256, 0, st>>>(a);
+    else     bwd_fused_finalize_kernel<<<(int)g, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -29,7 +29,7 @@ __global__ void publish_kernel(const float* __restrict__ src, int64_t ld, int b_
 }
 
 template <bool kParts>
-__global__ void prep_kernel(const PrepArgs a) {
+__global__ void prep_scalar_kernel(const PrepArgs a) {
     const int64_t n_col = (int64_t)a.bg_pad * a.dp, n_row = (int64_t)a.bl_pad * a.dp;
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket = 0u;
     // ---- rows first (local data only): per-(i,d) constants, optionally the fused reparameterize
@@ -74,6 +74,74 @@ __global__ void prep_kernel(const PrepArgs a) {
             }
         }
         a.mu_pad[idx] = v;
+    }
+}
+
+__device__ __forceinline__ float4 ld_volatile_v4(const float* p) {          // peer-mapped memory: no L1 / nc path
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// The same prologue with 16-byte accesses: launched when d % 4 == 0 and every caller-side pitch / pointer is 16-byte aligned
+// (the encoder's chunk views and dense tensors both are, for D % 4 == 0); prep_scalar_kernel covers the rest.
+template <bool kParts>
+__global__ void prep_kernel(const PrepArgs a) {
+    const int dp4 = a.dp / 4;
+    const int64_t n_col = (int64_t)a.bg_pad * dp4, n_row = (int64_t)a.bl_pad * dp4;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket = 0u;
+    auto ld4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_row; k += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(k / dp4), dd = 4 * (int)(k % dp4);
+        float o_zs[4] = {0.f, 0.f, 0.f, 0.f}, o_ns[4] = {0.f, 0.f, 0.f, 0.f}, o_q[4] = {0.f, 0.f, 0.f, 0.f}, o_sh[4] = {0.f, 0.f, 0.f, 0.f},
+              o_vr[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i < a.b_loc && dd < a.d) {
+            const float4 lv4 = ld4(a.logvar + (int64_t)i * a.ldlv + dd);
+            const float lvv[4] = {lv4.x, lv4.y, lv4.z, lv4.w};
+            float zv[4];
+            if (a.eps != nullptr) {                                     // fused reparameterize, ops.py:183-185
+                const float4 m4 = ld4(a.mu_loc + (int64_t)i * a.ldmu_loc + dd), e4 = ld4(a.eps + (int64_t)i * a.ldeps + dd);
+                const float mv[4] = {m4.x, m4.y, m4.z, m4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) zv[e] = mv[e] + ev[e] * expf(0.5f * lvv[e]);
+                if (a.z_out != nullptr) *reinterpret_cast<float4*>(a.z_out + (int64_t)i * a.ldz_out + dd) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+            } else {
+                const float4 z4 = ld4(a.z + (int64_t)i * a.ldz + dd);
+                zv[0] = z4.x; zv[1] = z4.y; zv[2] = z4.z; zv[3] = z4.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float var = expf(lvv[e]);
+                const float vc = (var < kVarFloor) ? kVarFloor : var;       // NaN stays NaN, like clamp_
+                const float iv = 1.0f / vc;
+                const float c = -0.5f * (logf(vc) + kLog2Pi);
+                const float sc = sqrtf(0.5f * kLog2e * iv);
+                o_zs[e] = zv[e] * sc;
+                o_ns[e] = -sc;
+                o_q[e] = fmaxf(0.0f, (50.0f + c) * kLog2e);
+                o_sh[e] = (c < kLogpFloor) ? kLogpFloor : c;
+                o_vr[e] = 0.5f * var * iv;                                  // straight-through floor: d/dlv uses the unclamped var
+            }
+        }
+        reinterpret_cast<float4*>(a.zs)[k] = make_float4(o_zs[0], o_zs[1], o_zs[2], o_zs[3]);
+        reinterpret_cast<float4*>(a.ns)[k] = make_float4(o_ns[0], o_ns[1], o_ns[2], o_ns[3]);
+        reinterpret_cast<float4*>(a.qmax)[k] = make_float4(o_q[0], o_q[1], o_q[2], o_q[3]);
+        reinterpret_cast<float4*>(a.shift)[k] = make_float4(o_sh[0], o_sh[1], o_sh[2], o_sh[3]);
+        reinterpret_cast<float4*>(a.vr)[k] = make_float4(o_vr[0], o_vr[1], o_vr[2], o_vr[3]);
+    }
+    if (kParts && a.sync.on()) peer_barrier(a.sync);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_col; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / dp4), dd = 4 * (int)(idx % dp4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < a.b_glob && dd < a.d) {
+            if (kParts) {
+                const int part = j / a.rows_per_part;
+                v = ld_volatile_v4(a.parts[part] + (int64_t)(j - part * a.rows_per_part) * a.ld_part + dd);      // 16-byte loads over NVLink
+            } else {
+                v = ld4(a.mu_all + (int64_t)j * a.ldmu + dd);
+            }
+        }
+        reinterpret_cast<float4*>(a.mu_pad)[idx] = v;
     }
 }
 
@@ -383,7 +451,6 @@ __global__ void bwd_prep_kernel(const BwdUpstream u, const float* __restrict__ S
                                 float* __restrict__ gps, float* __restrict__ gj, float* __restrict__ gk,
                                 float* __restrict__ zero, int64_t zero_n) {
     const int64_t n = (int64_t)bl_pad * dp;
-    const int64_t total = n > zero_n ? n : zero_n;
     const float inv_b = 1.0f / (float)b_loc;
     const float gl_mean = u.g_loss_mean ? u.g_loss_mean[0] * inv_b : 0.0f;
     const float gk_mean = u.g_kl_mean ? u.g_kl_mean[0] * inv_b : 0.0f;
@@ -393,32 +460,36 @@ __global__ void bwd_prep_kernel(const BwdUpstream u, const float* __restrict__ S
         g_rec = u.g_expelbo ? ge * u.e_rows[i] : 0.0f;
         return (u.g_loss ? u.g_loss[i] : 0.0f) + gl_mean + g_rec;
     };
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        if (idx < zero_n) zero[idx] = 0.0f;
-        if (idx >= n) continue;
-        const int i = (int)(idx / dp);
-        float gP = 0.0f;
+    // all arrays here are the library's own ([rows][dp] with dp % 32 == 0, 256-byte aligned): 16-byte accesses throughout
+    const int64_t n4 = n / 4, zero4 = zero_n / 4, total4 = n4 > zero4 ? n4 : zero4;
+    const int dp4 = dp / 4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (idx < zero4) reinterpret_cast<float4*>(zero)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx >= n4) continue;
+        const int i = (int)(idx / dp4);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < b_loc) {
-            float g_rec;
+            float g_rec, gP = 0.0f;
             if (u.g_log_qz_prod) gP += u.g_log_qz_prod[i];
             gP -= (u.beta - 1.0f) * g_loss_of(i, g_rec);
-            gP /= S[idx];
+            const float4 sv = reinterpret_cast<const float4*>(S)[idx];
+            o = make_float4(gP / sv.x, gP / sv.y, gP / sv.z, gP / sv.w);
         }
-        gps[idx] = gP;
-        if (idx < bl_pad) {
-            float gJ = 0.0f, k = 0.0f;
-            if (idx < b_loc) {
-                float g_rec;
-                const float gl = g_loss_of((int)idx, g_rec);
-                if (u.g_log_qz) gJ += u.g_log_qz[idx];
-                gJ += (u.beta - 1.0f) * gl;
-                k = gl + gk_mean;
-                if (u.g_kl) k += u.g_kl[idx];
-                if (u.g_rec_rows) u.g_rec_rows[idx] = g_rec;
-            }
-            gj[idx] = gJ;
-            if (gk) gk[idx] = k;
+        reinterpret_cast<float4*>(gps)[idx] = o;
+    }
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < bl_pad; idx += (int64_t)gridDim.x * blockDim.x) {
+        float gJ = 0.0f, k = 0.0f;
+        if (idx < b_loc) {
+            float g_rec;
+            const float gl = g_loss_of((int)idx, g_rec);
+            if (u.g_log_qz) gJ += u.g_log_qz[idx];
+            gJ += (u.beta - 1.0f) * gl;
+            k = gl + gk_mean;
+            if (u.g_kl) k += u.g_kl[idx];
+            if (u.g_rec_rows) u.g_rec_rows[idx] = g_rec;
         }
+        gj[idx] = gJ;
+        if (gk) gk[idx] = k;
     }
 }
 
@@ -455,11 +526,22 @@ cudaError_t launch_publish(const float* src, int64_t ld, int b_loc, int d, float
     return cudaGetLastError();
 }
 
+static inline bool aligned16(const void* p, int64_t ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ld % 4 == 0); }
+
 cudaError_t launch_prep(const PrepArgs& a, cudaStream_t st) {
-    const int64_t n = ((int64_t)a.bg_pad + a.bl_pad) * a.dp;
+    const bool vec = a.d % 4 == 0 && aligned16(a.mu_all, a.ldmu) && aligned16(a.z, a.ldz) && aligned16(a.eps, a.ldeps)
+                     && aligned16(a.mu_loc, a.ldmu_loc) && aligned16(a.z_out, a.ldz_out) && aligned16(a.logvar, a.ldlv)
+                     && (a.parts == nullptr || a.ld_part % 4 == 0);          // the ranks' published buffers are dense, 16-byte aligned allocations
     LaunchScope scope(kKernNone, st);
-    if (a.parts != nullptr) prep_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(a);
-    else                    prep_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(a);
+    if (vec) {
+        const int64_t n = (int64_t)(a.bg_pad > a.bl_pad ? a.bg_pad : a.bl_pad) * (a.dp / 4);
+        if (a.parts != nullptr) prep_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(a);
+        else                    prep_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(a);
+    } else {
+        const int64_t n = (int64_t)(a.bg_pad > a.bl_pad ? a.bg_pad : a.bl_pad) * a.dp;
+        if (a.parts != nullptr) prep_scalar_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(a);
+        else                    prep_scalar_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -493,7 +575,7 @@ cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st
 cudaError_t launch_bwd_prep(const Plan& p, const BwdUpstream& u, const float* S, float* gps, float* gj, float* gk,
                             float* zero, size_t zero_n, cudaStream_t st) {
     const int64_t n = (int64_t)p.bl_pad * p.dp;
-    const int64_t total = n > (int64_t)zero_n ? n : (int64_t)zero_n;
+    const int64_t total = (n > (int64_t)zero_n ? n : (int64_t)zero_n) / 4;        // one float4 per thread and pass
     LaunchScope scope(kKernNone, st);
     bwd_prep_kernel<<<grid_for(total, 256), 256, 0, st>>>(u, S, p.b_loc, p.bl_pad, p.dp, gps, gj, gk, zero, (int64_t)zero_n);
     return cudaGetLastError();
