@@ -249,9 +249,8 @@ def _finite_relerr(a, b):
 @pytest.mark.parametrize("what", ["mu_nan", "mu_pinf", "mu_ninf", "lv_nan", "lv_pinf", "lv_ninf", "lv_huge", "lv_tiny"])
 def test_non_finite_inputs_propagate_like_the_reference(B, D, what):
     """the op must propagate NaN / Inf like the reference, not trap or launder them.
-    One poisoned element (row i0, dim d0).  Every loss term must carry NaN / +Inf / -Inf at exactly the reference's
-    positions and agree elsewhere; gradients must agree wherever both are finite and never turn a reference NaN into a
-    number (in rows that are already NaN the kernels' multiplicative clamp mask gives NaN where torch's where() gives 0)."""
+    One poisoned element (row i0, dim d0).  Every loss term and both gradients must carry NaN / +Inf / -Inf at exactly the
+    reference's positions and agree elsewhere."""
     ops = _ops()
     N, beta = 16704, 6.0
     mu_c, lv_c, eps_c = _latents(B, D, "base", seed=13)
@@ -277,11 +276,10 @@ def test_non_finite_inputs_propagate_like_the_reference(B, D, what):
         assert _same_pattern(got, want), f"{what}: non-finite pattern of {name} differs from the reference"
         assert _finite_relerr(got, want) < LOSS_RTOL, f"{what}: finite entries of {name}"
     for name, got, want in (("dmu", mu.grad, mu_o.grad), ("dlv", lv.grad, lv_o.grad)):
-        g_nan, w_nan = torch.isnan(got).cpu(), torch.isnan(want)
-        assert bool((g_nan | ~w_nan).all()), f"{what}: {name} is finite where the reference's is NaN"
+        # the clamp mask is a select in the sweep (like the where() of torch.clamp's backward), so the gradients carry NaN / Inf at
+        # exactly the reference's positions, rows that are already NaN included
+        assert _same_pattern(got, want), f"{what}: non-finite pattern of {name} differs from the reference"
         assert _finite_relerr(got, want) < GRAD_RTOL, f"{what}: finite entries of {name}"
-        if bool(torch.isfinite(loss_o).all()):                    # no NaN row anywhere: the patterns must then agree exactly
-            assert _same_pattern(got, want), f"{what}: non-finite pattern of {name} differs from the reference"
     record("non_finite", f"{what}_B{B}_D{D}", loss=_finite_relerr(loss, loss_o), dmu=_finite_relerr(mu.grad, mu_o.grad),
            dlv=_finite_relerr(lv.grad, lv_o.grad), extra_nan_dmu=float((torch.isnan(mu.grad).cpu() & ~torch.isnan(mu_o.grad)).sum()),
            extra_nan_dlv=float((torch.isnan(lv.grad).cpu() & ~torch.isnan(lv_o.grad)).sum()))

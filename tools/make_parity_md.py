@@ -32,9 +32,9 @@ for test in sorted(worst):
             continue
         gate = 1e-5 if k in LOSS else 1e-4
         out.append(f"| {test} | {k} | {v:.2e} | {gate:.0e} | {case} |")
-out += ["", "`extra_nan_*`: number of gradient entries that are NaN here but 0 in the reference, in rows whose loss is already NaN (one poisoned",
-        "input element).  The reference's clamp mask is a `where`, which turns a NaN coefficient of a clamped element into 0; the sweep",
-        "applies the mask by select as well, but a NaN joint coefficient (the row's `log_qz` is NaN) still reaches the unclamped elements",
-        "of that row and, through the column sums, every `grad_mu` entry the row contributes to.  No reference NaN ever becomes a number.", ""]
+out += ["", "`extra_nan_*`: number of gradient entries that are NaN here but not in the reference, over the non-finite-input cases (one poisoned",
+        "element of mu or logvar: NaN, +Inf, -Inf, logvar = 80, logvar = -120).  It is 0: the sweep applies the -50 clamp's gradient mask by select,",
+        "like the `where` of `torch.clamp`'s backward, so NaN / Inf appear at exactly the reference's positions in every loss term and gradient",
+        "(`tests/test_parity_gaps_gpu.py::test_non_finite_inputs_propagate_like_the_reference` asserts the pattern equality).", ""]
 open(os.path.join(ROOT, "profiles", "r2_parity.md"), "w").write("\n".join(out))
 print("\n".join(out))
