@@ -553,19 +553,11 @@ static cudaError_t launch_bwd_ds(const Plan& p, const BwdFusedArgs& a, BwdFinArg
         return launch_bwd_ds_t<2, 1, 8, 2, 16, 8, false, true>(p, a, fin, st);
     }
     if (p.dp >= 128) {
-        switch (variant) {
-            case 1:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 8>(p, a, fin, st);               // 12 rows/warp, 16 warps/SM, mask by multiply
-            case 2:  return launch_bwd_ds_t<8, 4, 12, 1, 16, 4>(p, a, fin, st);              // 4 columns per basic block, mask by multiply
-            case 3:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 4, true>(p, a, fin, st);         // two columns in lockstep
-            case 4:  return launch_bwd_ds_t<5, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);  // 10 rows/warp, 16 warps/SM
-            case 5:  return launch_bwd_ds_t<8, 4, 12, 1, 16, 16, false, true>(p, a, fin, st);  // the whole tile in one basic block
-            case 6:  return launch_bwd_ds_t<8, 4, 12, 1, 32, 8, false, true>(p, a, fin, st);   // 32-column tiles
-            case 7:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);
-            case 8:  return launch_bwd_ds_t<4, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);
-            case 9:  return launch_bwd_ds_t<9, 4, 12, 1, 16, 8, false, true>(p, a, fin, st);   // 18 rows/warp
-            case 10: return launch_bwd_ds_t<7, 4, 12, 1, 16, 8, false, true>(p, a, fin, st);   // 14 rows/warp
-            case 11: return launch_bwd_ds_t<8, 4, 12, 1, 16, 8>(p, a, fin, st);                // mask by multiply
-            case 12: return launch_bwd_ds_t<10, 4, 8, 1, 16, 8, false, true>(p, a, fin, st);   // 20 rows/warp, 8 warps/SM, 255 regs
+        switch (variant) {           // tools/tune_bwd.py: the tuning points that bracket the shipped one (profiles/r2_bwd_ds_sweep.md)
+            case 1:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);    // 12 rows/warp, 16 warps/SM (128 regs)
+            case 2:  return launch_bwd_ds_t<5, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);    // 10 rows/warp, 16 warps/SM
+            case 3:  return launch_bwd_ds_t<8, 4, 12, 1, 16, 8>(p, a, fin, st);                // shipped shape, clamp mask by multiply
+            case 4:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 4, true>(p, a, fin, st);           // two columns in lockstep
             default: return launch_bwd_ds_t<8, 4, 12, 1, 16, 8, false, true>(p, a, fin, st);   // 16 rows/warp, 12 warps/SM (168 regs),
         }                                                                                       // 8 columns per basic block, mask by select
     }

@@ -152,3 +152,64 @@ def test_graphed_soft_intro_step_matches_the_reference_train_step(capture):
         u_got = torch.cat([(p.detach() - p0).flatten() for p, p0 in zip(model.parameters(), init_params)])
         cos = torch.dot(u_ref, u_got) / (u_ref.norm() * u_got.norm())
         assert cos.item() > 0.99, (capture, cos.item())
+
+
+def test_train_step_throughput_reference_vs_dropin_vs_graphed_step():
+    """BASELINE configs[1] shape (64x64x3 images, conv arch with channels 64-128-256-512, z_dim 128, batch 64) on the reference's own
+    SoftIntroVAE: images/s of (a) the untouched reference's IntroTCSovler.train_step in eager torch on this GPU, (b) the same
+    train_step after install() (loss terms on the kernels), (c) SoftIntroTCStep (two CUDA graphs, no host synchronisation).
+    Recorded in gpurun_out/r2_train_dropin.json; the kernels must not make the reference's own step slower."""
+    import json
+    import os
+    import time
+    dev = torch.device("cuda:0")
+    B, steps = 64, 8
+    batch = torch.rand(B, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    out = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return B * steps / (time.perf_counter() - t0)
+
+    for installed in (False, True):
+        with ref_loader.on_path():
+            import models
+            if installed:
+                import intro_tc_vae_b200
+                intro_tc_vae_b200.install()
+            from solvers.intro_tc import IntroTCSovler
+            from utils import SingletonWriter
+            SingletonWriter().writer, SingletonWriter().cur_iter = None, 0
+            torch.manual_seed(0)
+            model = models.SoftIntroVAE(arch="conv", cdim=3, zdim=128, channels=(64, 128, 256, 512), image_size=64).to(dev)
+            opt_e = torch.optim.Adam(model.encoder.parameters(), lr=2e-4)
+            opt_d = torch.optim.Adam(model.decoder.parameters(), lr=2e-4)
+            solver = IntroTCSovler(dataset=_Dataset(), model=model, batch_size=B, optimizer_e=opt_e, optimizer_d=opt_d, recon_loss_type="mse",
+                                   beta_kl=0.5, beta_rec=0.75, beta_neg=512.0, gamma_r=1e-8, device=dev, use_amp=False, grad_scaler=None,
+                                   writer=None, test_iter=1000, clip=100.0)
+            out["installed_reference_train_step" if installed else "untouched_reference_train_step"] = timed(lambda: solver.train_step(batch, 0))
+            if installed:
+                from intro_tc_vae_b200.train_step import SoftIntroTCStep
+                torch.manual_seed(0)
+                model2 = models.SoftIntroVAE(arch="conv", cdim=3, zdim=128, channels=(64, 128, 256, 512), image_size=64).to(dev)
+                oe = torch.optim.Adam(model2.encoder.parameters(), lr=2e-4, capturable=True)
+                od = torch.optim.Adam(model2.decoder.parameters(), lr=2e-4, capturable=True)
+                step = SoftIntroTCStep(model2, oe, od, N_DATA, batch.shape, recon_loss_type="mse", beta_kl=0.5, beta_rec=0.75, beta_neg=512.0,
+                                       gamma_r=1e-8, clip=100.0)
+                real, noise = batch.to(dev), torch.randn(B, 128, device=dev)
+                out["graphed_soft_intro_step"] = timed(lambda: step(real, noise))
+                step.check_finite()
+    out = {k: round(v, 1) for k, v in out.items()}
+    out["unit"] = "images/s, one B200, 64x64x3, conv arch, z_dim 128, batch 64, fp32"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "r2_train_dropin.json"), "w") as f:
+        json.dump(out, f)
+    assert out["installed_reference_train_step"] > 0.9 * out["untouched_reference_train_step"], out
+    assert out["graphed_soft_intro_step"] > out["installed_reference_train_step"], out
