@@ -150,14 +150,14 @@ __global__ void prep_kernel(const PrepArgs a) {
 // {l + LPR*k}, k = 0..7), so a warp covers 32/LPR rows and the d-sum of a pair (i,j) needs only
 // log2(LPR) shuffles.  grid = (row blocks, column splits); partial results go to the workspace.
 // =====================================================================================================
-template <int LPR, bool kWeighted>
+template <int LPR, bool kWeighted, int KCH>
 __device__ __forceinline__ float fwd_one_column(const float* __restrict__ mu_row,   // smem row of column j, + 4*l
-                                                 const u64 (&zs2)[16], const u64 (&ns2)[16], const float (&qmx)[32],
-                                                 u64 (&S2)[16], float rho) {
+                                                 const u64 (&zs2)[2 * KCH], const u64 (&ns2)[2 * KCH], const float (&qmx)[4 * KCH],
+                                                 u64 (&S2)[2 * KCH], float rho) {
     u64 acc0 = 0ull, acc1 = 0ull;
     const u64 rho2 = pack2(rho, rho);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < KCH; ++k) {
         const float4 m = *reinterpret_cast<const float4*>(mu_row + 4 * LPR * k);
         const u64 d01 = ffma2(pack2(m.x, m.y), ns2[2 * k], zs2[2 * k]);
         const u64 d23 = ffma2(pack2(m.z, m.w), ns2[2 * k + 1], zs2[2 * k + 1]);
@@ -180,11 +180,11 @@ __device__ __forceinline__ float fwd_one_column(const float* __restrict__ mu_row
     return a + b;
 }
 
-template <int LPR, bool kSpecial>
+template <int LPR, bool kSpecial, int KCH>
 __device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt, int jt0, int l, int i_glob, bool row_store,
-                                         const Weights& w, const u64 (&zs2)[16], const u64 (&ns2)[16], const float (&qmx)[32],
-                                         u64 (&S2)[16], float& lse_m, float& lse_s, float* __restrict__ s2_row) {
-    constexpr int DP = 32 * LPR;
+                                         const Weights& w, const u64 (&zs2)[2 * KCH], const u64 (&ns2)[2 * KCH], const float (&qmx)[4 * KCH],
+                                         u64 (&S2)[2 * KCH], float& lse_m, float& lse_s, float* __restrict__ s2_row) {
+    constexpr int DP = 4 * KCH * LPR;
     constexpr int G = LPR < 4 ? LPR : 4;
     for (int jj = 0; jj < jt; jj += 4) {
         float part[4];
@@ -192,7 +192,7 @@ __device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt,
         for (int u = 0; u < 4; ++u) {
             float rho = 1.0f, l2 = 0.0f;
             if (kSpecial) weight_of(w, i_glob, jt0 + jj + u, rho, l2);
-            part[u] = fwd_one_column<LPR, kSpecial>(tile + (jj + u) * DP + 4 * l, zs2, ns2, qmx, S2, rho);
+            part[u] = fwd_one_column<LPR, kSpecial, KCH>(tile + (jj + u) * DP + 4 * l, zs2, ns2, qmx, S2, rho);
         }
 #pragma unroll
         for (int o = 1; o < LPR; o <<= 1) {
@@ -222,10 +222,12 @@ __device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt,
     }
 }
 
-template <int LPR, int JTS>     // JTS: columns per tile (0 = as many as fit kTileFloats, at most 32)
-__global__ void __launch_bounds__(kFwdWarps * 32, 3)
+// JTS: columns per tile (0 = as many as fit kTileFloats, at most 32); KCH: 16-byte chunks (4 dims) per lane -- 8 in the shipped
+// mapping (32 dims per lane), 4 in the tuning point that trades shuffles for twice the resident warps; MINB: CTAs per SM
+template <int LPR, int JTS, int KCH = 8, int MINB = 3>
+__global__ void __launch_bounds__(kFwdWarps * 32, MINB)
 tc_fwd_kernel(const FwdArgs a) {
-    constexpr int DP = 32 * LPR;
+    constexpr int DP = 4 * KCH * LPR;
     constexpr int RPW = 32 / LPR;
     constexpr int ROWS = kFwdWarps * RPW;
     constexpr int JT = JTS > 0 ? JTS : ((kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP));
@@ -250,8 +252,8 @@ tc_fwd_kernel(const FwdArgs a) {
     int row = rb * ROWS + warp * RPW + rw;                                   // < bl_pad by construction
     const bool row_valid = true;   // padded rows hold finite zeros: store their s2 too so backward never reads garbage
 
-    u64 zs2[16], ns2[16], S2[16];
-    float qmx[32];
+    u64 zs2[2 * KCH], ns2[2 * KCH], S2[2 * KCH];
+    float qmx[4 * KCH];
     float lse_m = kNegBig, lse_s = 0.0f;
     // ---- this thread's slice of the row constants -> registers
     auto load_row = [&]() {
@@ -259,7 +261,7 @@ tc_fwd_kernel(const FwdArgs a) {
         const float* pn = a.ns + (size_t)row * DP + 4 * l;
         const float* pq = a.qmax + (size_t)row * DP + 4 * l;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < KCH; ++k) {
             const float4 vz = __ldg(reinterpret_cast<const float4*>(pz + 4 * LPR * k));
             const float4 vn = __ldg(reinterpret_cast<const float4*>(pn + 4 * LPR * k));
             const float4 vq = __ldg(reinterpret_cast<const float4*>(pq + 4 * LPR * k));
@@ -275,7 +277,7 @@ tc_fwd_kernel(const FwdArgs a) {
         const int slot = (int)blockIdx.x - seg_of(a.seg, (int64_t)rb * T);
         float* ps = a.Spart + ((size_t)slot * a.bl_pad + row) * DP + 4 * l;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < KCH; ++k) {
             float4 v;
             unpack2(S2[2 * k], v.x, v.y); unpack2(S2[2 * k + 1], v.z, v.w);
             *reinterpret_cast<float4*>(ps + 4 * LPR * k) = v;
@@ -323,8 +325,8 @@ tc_fwd_kernel(const FwdArgs a) {
         const bool special = (a.w.mss && jt0 == 0) || (jt0 + JT > a.w.b_glob);
         float* s2_row = (a.s2 != nullptr) ? a.s2 + (size_t)row * a.ld_s2 : nullptr;
         const int i_glob = a.row_offset + row;
-        if (special) fwd_tile<LPR, true>(tile, JT, jt0, l, i_glob, row_valid, a.w, zs2, ns2, qmx, S2, lse_m, lse_s, s2_row);
-        else         fwd_tile<LPR, false>(tile, JT, jt0, l, i_glob, row_valid, a.w, zs2, ns2, qmx, S2, lse_m, lse_s, s2_row);
+        if (special) fwd_tile<LPR, true, KCH>(tile, JT, jt0, l, i_glob, row_valid, a.w, zs2, ns2, qmx, S2, lse_m, lse_s, s2_row);
+        else         fwd_tile<LPR, false, KCH>(tile, JT, jt0, l, i_glob, row_valid, a.w, zs2, ns2, qmx, S2, lse_m, lse_s, s2_row);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[st]);
     }
@@ -503,20 +505,20 @@ static inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
     return (int)g;
 }
 
-template <int LPR, int JTS>
+template <int LPR, int JTS, int KCH = 8, int MINB = 3>
 static cudaError_t launch_fwd_t(const Plan& p, const FwdArgs& a, cudaStream_t st) {
-    constexpr int DP = 32 * LPR;
+    constexpr int DP = 4 * KCH * LPR;
     constexpr int JT = JTS > 0 ? JTS : ((kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP));
     const size_t smem = (size_t)kStages * JT * DP * sizeof(float) + 2 * kStages * sizeof(uint64_t);
     static PerDevice configured_on;
     int& configured = configured_on.cur();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<LPR, JTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<LPR, JTS, KCH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = 1;
     }
     LaunchScope scope(kKernFwd, st);
-    tc_fwd_kernel<LPR, JTS><<<p.seg_fwd.n_ctas, kFwdWarps * 32, smem, st>>>(a);
+    tc_fwd_kernel<LPR, JTS, KCH, MINB><<<p.seg_fwd.n_ctas, kFwdWarps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -555,6 +557,10 @@ cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st) {
             case 16: return launch_fwd_t<16, kSmallTile>(p, a, st);
             default: return cudaErrorInvalidValue;
         }
+    }
+    if (p.fwd_lpr8) {                    // tuning point: 8 lanes per row x 16 dims per lane at D = 128 (16 rows per CTA)
+        if (p.fwd_lpr8 == 2) return launch_fwd_t<8, 0, 4, 5>(p, a, st);
+        return launch_fwd_t<8, 0, 4, 4>(p, a, st);
     }
     switch (p.dpt) {
         case 1:  return launch_fwd_t<1, 0>(p, a, st);

@@ -66,6 +66,7 @@ struct Plan {
     // backward scratch (its own buffer, so the forward workspace stays immutable and backward can be re-run)
     size_t boff_gps, boff_gj, boff_gk, boff_A, boff_CR, boff_G, bwd_bytes;
     bool save, var_col;
+    int fwd_lpr8;              // tuning: forward sweep with 8 lanes per row / 16 dims per lane at dp == 128 (0 = shipped mapping)
     bool small;                // fewer work units than SMs with the standard tiles: small-tile / few-rows instantiations
 };
 
@@ -108,7 +109,8 @@ inline Segments plan_segments(int64_t n_blocks, int tiles_per_block, int slots, 
     return s;
 }
 
-inline int& fwd_seg_target() { static int v = 0; return v; }   // tuning: forward segment length in column tiles (0 = default)
+inline int& fwd_seg_target() { static int v = 0; return v; }
+inline int& fwd_lpr8_tuning() { static int v = 0; return v; }   // tools/tune_bwd.py --fwd-lpr8   // tuning: forward segment length in column tiles (0 = default)
 
 // `sms` = multiprocessor count of the current device (148 on B200).
 inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int sms) {
@@ -120,7 +122,8 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.save = (flags & 4u) != 0;
     p.var_col = (flags & 2u) != 0;
     // ---- forward: a CTA owns fwd_rows rows and a contiguous range of columns
-    p.fwd_rows = kFwdWarps * (32 / p.dpt);
+    p.fwd_lpr8 = (!p.var_col && dp == 128) ? fwd_lpr8_tuning() : 0;
+    p.fwd_rows = kFwdWarps * (32 / (p.fwd_lpr8 ? 8 : p.dpt));
     // rows pad to whole forward row blocks (32 rows at D >= 128), columns to whole 32-column tiles; the column-variance sweeps
     // keep the 128-row padding their uniform grids were written for
     const int row_pad = p.var_col ? kRowPad : (p.fwd_rows > kColPad ? p.fwd_rows : kColPad);
@@ -131,7 +134,7 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.n_rb_fwd = p.bl_pad / p.fwd_rows;
     // small problems (BASELINE cfg 1 / 2: B = 3 / 64): 4-column tiles, so that row blocks x tiles still gives every SM a CTA
     p.small = !p.var_col && (int64_t)p.n_rb_fwd * (p.bg_pad / p.jt) < sms;
-    if (p.small) p.jt = kSmallTile;
+    if (p.small) { p.jt = kSmallTile; if (p.fwd_lpr8) { p.fwd_lpr8 = 0; p.fwd_rows = kFwdWarps * (32 / p.dpt); p.n_rb_fwd = p.bl_pad / p.fwd_rows; } }
     choose_splits(p.n_rb_fwd, sms * 3, p.bg_pad, p.jt, 4, p.n_js_fwd, p.js_len_fwd);   // 3 resident CTAs per SM
     p.tiles_fwd = p.bg_pad / p.jt;
     p.seg_fwd = plan_segments(p.n_rb_fwd, p.tiles_fwd, sms * 3, fwd_seg_target() > 0 ? fwd_seg_target() : 21);

@@ -1,14 +1,17 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 2400 python -m pytest tests -m gpu -q --timeout=1500 > gpurun_out/r2o_pytest.log 2>&1
-tail -4 gpurun_out/r2o_pytest.log
-timeout 300 python tools/tune_bwd.py --variants=0 --reps 9 --rows 1024 --fwd-seg 0 > gpurun_out/r2o_tune_1024.log 2>&1; cat gpurun_out/r2o_tune_1024.log
-timeout 300 python tools/tune_bwd.py --variants=0 --reps 7 --fwd-seg 0 > gpurun_out/r2o_tune_8192.log 2>&1; cat gpurun_out/r2o_tune_8192.log
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r2o_bench_n1.json 2> gpurun_out/r2o_bench.err
-tail -3 gpurun_out/r2o_bench.err
+for N in 8 4 2; do
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2p_bench_n$N.json 2> gpurun_out/r2p_bench_n$N.err
+tail -2 gpurun_out/r2p_bench_n$N.err
 python -c "
-import json;j=json.load(open('gpurun_out/r2o_bench_n1.json'))
-print({k:j[k] for k in ('ms_per_step','value','gpu_launches')}, j['e2e']['ms_per_step'], j['dropin']['ms_per_step'], j['e2e_dropin']['ms_per_step'], j['roofline']['kernel_ms'], j['roofline']['step_frac_of_sfu_peak'], j['roofline']['traffic'], j['train']['value'])
+import json;j=json.loads([l for l in open('gpurun_out/r2p_bench_n$N.json') if l.startswith('{')][-1])
+print($N, {k:j[k] for k in ('ms_per_step','value','gpu_launches')}, j['e2e']['ms_per_step'], j['dropin']['ms_per_step'], j['e2e_dropin']['ms_per_step'], j['roofline']['kernel_ms'], (j['train'] or {}).get('value'))
 "
-timeout 300 python tools/small_batch_bench.py --batch 64 > gpurun_out/r2o_small64.json 2>/dev/null; cat gpurun_out/r2o_small64.json
+done
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 10 --warmup 3 --batch 32768 --zdim 512 --no-train > gpurun_out/r2p_bench_cfg4_n8.json 2> gpurun_out/r2p_bench_cfg4_n8.err
+python -c "
+import json;j=json.loads([l for l in open('gpurun_out/r2p_bench_cfg4_n8.json') if l.startswith('{')][-1])
+print('cfg4', {k:j[k] for k in ('ms_per_step','value')}, j['e2e']['ms_per_step'], j['roofline']['kernel_ms'])
+"
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 tools/train_bench.py --image 64 --zdim 128 --batch 64 --peer > gpurun_out/r2p_train_n8_64.json 2> gpurun_out/r2p_train_n8_64.err; cat gpurun_out/r2p_train_n8_64.json | cut -c1-300
