@@ -566,7 +566,8 @@ int tcelbo_set_tuning(const char* key, int value) {
     if (key && std::strcmp(key, "bwd_variant") == 0) { set_bwd_variant(value); return TCELBO_OK; }
     if (key && std::strcmp(key, "fwd_seg_tiles") == 0) { fwd_seg_target() = value; return TCELBO_OK; }
     if (key && std::strcmp(key, "bwd_seg_tiles") == 0) { set_bwd_seg_target(value); return TCELBO_OK; }
-    if (key && std::strcmp(key, "fwd_lpr8") == 0) { fwd_lpr8_tuning() = value; return TCELBO_OK; }
+    if (key && std::strcmp(key, "fwd_map") == 0) { fwd_map_tuning() = value; return TCELBO_OK; }
+    if (key && std::strcmp(key, "fwd_wave") == 0) { fwd_wave_tuning() = value; return TCELBO_OK; }
     return fail(TCELBO_ERR_INVALID, "unknown tuning key");
 }
 

@@ -146,8 +146,8 @@ __global__ void prep_kernel(const PrepArgs a) {
 }
 
 // =====================================================================================================
-// Forward sweep.  LPR lanes share one row (each lane owns 32 of the row's dims: 16-byte chunks
-// {l + LPR*k}, k = 0..7), so a warp covers 32/LPR rows and the d-sum of a pair (i,j) needs only
+// Forward sweep.  LPR lanes share one row (each lane owns 4*KCH of the row's dims: 16-byte chunks
+// {l + LPR*k}, k = 0..KCH-1), so a warp covers 32/LPR rows and the d-sum of a pair (i,j) needs only
 // log2(LPR) shuffles.  grid = (row blocks, column splits); partial results go to the workspace.
 // =====================================================================================================
 template <int LPR, bool kWeighted, int KCH>
@@ -186,10 +186,13 @@ __device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt,
                                          u64 (&S2)[2 * KCH], float& lse_m, float& lse_s, float* __restrict__ s2_row) {
     constexpr int DP = 4 * KCH * LPR;
     constexpr int G = LPR < 4 ? LPR : 4;
-    for (int jj = 0; jj < jt; jj += 4) {
-        float part[4];
+    // columns per iteration: after the butterfly every lane of a row keeps ONE column's joint exponent; with 8 lanes per row and
+    // 16 dims per lane (KCH == 4) 8 columns are in flight so that no two lanes keep the same one
+    constexpr int NC = (LPR >= 8 && KCH == 4) ? 8 : 4;
+    for (int jj = 0; jj < jt; jj += NC) {
+        float part[NC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NC; ++u) {
             float rho = 1.0f, l2 = 0.0f;
             if (kSpecial) weight_of(w, i_glob, jt0 + jj + u, rho, l2);
             part[u] = fwd_one_column<LPR, kSpecial, KCH>(tile + (jj + u) * DP + 4 * l, zs2, ns2, qmx, S2, rho);
@@ -197,16 +200,18 @@ __device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt,
 #pragma unroll
         for (int o = 1; o < LPR; o <<= 1) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+            for (int u = 0; u < NC; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
         }
         if (LPR >= 4) {
-            const int u = l & 3;
-            const float mine = (u == 0) ? part[0] : (u == 1) ? part[1] : (u == 2) ? part[2] : part[3];
+            const int u = l & (NC - 1);
+            float mine = part[0];
+#pragma unroll
+            for (int v = 1; v < NC; ++v) mine = (u == v) ? part[v] : mine;
             const int j = jt0 + jj + u;
             float x = -mine;
             if (kSpecial) { float rho, l2; weight_of(w, i_glob, j, rho, l2); x += l2; }
             lse2_push(lse_m, lse_s, x);
-            if (s2_row != nullptr && row_store && l < 4) s2_row[j] = mine;
+            if (s2_row != nullptr && row_store && l < NC) s2_row[j] = mine;
         } else {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -222,8 +227,9 @@ __device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt,
     }
 }
 
-// JTS: columns per tile (0 = as many as fit kTileFloats, at most 32); KCH: 16-byte chunks (4 dims) per lane -- 8 in the shipped
-// mapping (32 dims per lane), 4 in the tuning point that trades shuffles for twice the resident warps; MINB: CTAs per SM
+// JTS: columns per tile (0 = as many as fit kTileFloats, at most 32); KCH: 16-byte chunks (4 dims) per lane -- 4 (16 dims per
+// lane, 128 registers, 4 CTAs per SM) for D <= 128, 8 (32 dims per lane, 168 registers, 3 CTAs per SM) for wider latents and for
+// the small-problem instantiation; MINB: CTAs per SM
 template <int LPR, int JTS, int KCH = 8, int MINB = 3>
 __global__ void __launch_bounds__(kFwdWarps * 32, MINB)
 tc_fwd_kernel(const FwdArgs a) {
@@ -283,7 +289,7 @@ tc_fwd_kernel(const FwdArgs a) {
             *reinterpret_cast<float4*>(ps + 4 * LPR * k) = v;
         }
 #pragma unroll
-        for (int o = 1; o < G; o <<= 1) {
+        for (int o = 1; o < ((LPR >= 8 && KCH == 4) ? 8 : G); o <<= 1) {      // lanes of a row that hold distinct partial logsumexps
             const float m2 = __shfl_xor_sync(0xffffffffu, lse_m, o);
             const float s2v = __shfl_xor_sync(0xffffffffu, lse_s, o);
             lse2_merge(lse_m, lse_s, m2, s2v);
@@ -558,9 +564,13 @@ cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st) {
             default: return cudaErrorInvalidValue;
         }
     }
-    if (p.fwd_lpr8) {                    // tuning point: 8 lanes per row x 16 dims per lane at D = 128 (16 rows per CTA)
-        if (p.fwd_lpr8 == 2) return launch_fwd_t<8, 0, 4, 5>(p, a, st);
-        return launch_fwd_t<8, 0, 4, 4>(p, a, st);
+    if (p.fwd_kch == 4) {                // D <= 128: 16 dims per lane, 4 CTAs per SM (<= 128 registers)
+        switch (p.fwd_lpr) {
+            case 2:  return launch_fwd_t<2, 0, 4, 4>(p, a, st);
+            case 4:  return launch_fwd_t<4, 0, 4, 4>(p, a, st);
+            case 8:  return launch_fwd_t<8, 0, 4, 4>(p, a, st);
+            default: return cudaErrorInvalidValue;
+        }
     }
     switch (p.dpt) {
         case 1:  return launch_fwd_t<1, 0>(p, a, st);

@@ -66,7 +66,7 @@ struct Plan {
     // backward scratch (its own buffer, so the forward workspace stays immutable and backward can be re-run)
     size_t boff_gps, boff_gj, boff_gk, boff_A, boff_CR, boff_G, bwd_bytes;
     bool save, var_col;
-    int fwd_lpr8;              // tuning: forward sweep with 8 lanes per row / 16 dims per lane at dp == 128 (0 = shipped mapping)
+    int fwd_lpr, fwd_kch;      // forward sweep mapping: lanes per row, 16-byte chunks (4 dims) per lane
     bool small;                // fewer work units than SMs with the standard tiles: small-tile / few-rows instantiations
 };
 
@@ -109,8 +109,9 @@ inline Segments plan_segments(int64_t n_blocks, int tiles_per_block, int slots, 
     return s;
 }
 
-inline int& fwd_seg_target() { static int v = 0; return v; }
-inline int& fwd_lpr8_tuning() { static int v = 0; return v; }   // tools/tune_bwd.py --fwd-lpr8   // tuning: forward segment length in column tiles (0 = default)
+inline int& fwd_seg_target() { static int v = 0; return v; }    // tuning: forward segment length in column tiles (0 = default)
+inline int& fwd_map_tuning() { static int v = 0; return v; }    // tools/tune_bwd.py --fwd-map: 1 = 32 dims per lane everywhere (round-1 mapping)
+inline int& fwd_wave_tuning() { static int v = 0; return v; }   // tuning: CTAs per SM the forward grid is sized for (0 = 3)
 
 // `sms` = multiprocessor count of the current device (148 on B200).
 inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int sms) {
@@ -122,22 +123,30 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.save = (flags & 4u) != 0;
     p.var_col = (flags & 2u) != 0;
     // ---- forward: a CTA owns fwd_rows rows and a contiguous range of columns
-    p.fwd_lpr8 = (!p.var_col && dp == 128) ? fwd_lpr8_tuning() : 0;
-    p.fwd_rows = kFwdWarps * (32 / (p.fwd_lpr8 ? 8 : p.dpt));
-    // rows pad to whole forward row blocks (32 rows at D >= 128), columns to whole 32-column tiles; the column-variance sweeps
-    // keep the 128-row padding their uniform grids were written for
-    const int row_pad = p.var_col ? kRowPad : (p.fwd_rows > kColPad ? p.fwd_rows : kColPad);
-    p.bl_pad = (int)round_up(b_loc, row_pad);
+    // forward mapping: lanes per row x 16-byte chunks per lane.  32 dims per lane (dp/32 lanes per row, 3 CTAs per SM) is the
+    // general one; D <= 128 uses 16 dims per lane (dp/16 lanes per row), which fits 4 CTAs per SM -- wider latents do not, because
+    // halving the rows per CTA doubles the L2 -> SM tile traffic.  Small problems (BASELINE cfg 1 / 2: B = 3 / 64) keep the general
+    // mapping with 4-column tiles, so that row blocks x tiles still gives every SM a CTA.
+    // Rows pad to whole forward row blocks, columns to whole 32-column tiles; the column-variance sweeps keep the 128-row padding
+    // their uniform grids were written for.
+    auto set_map = [&](int lpr, int kch) {
+        p.fwd_lpr = lpr; p.fwd_kch = kch;
+        p.fwd_rows = kFwdWarps * (32 / lpr);
+        const int row_pad = p.var_col ? kRowPad : (p.fwd_rows > kColPad ? p.fwd_rows : kColPad);
+        p.bl_pad = (int)round_up(b_loc, row_pad);
+        p.n_rb_fwd = p.bl_pad / p.fwd_rows;
+    };
+    set_map(p.dpt, 8);
     p.bg_pad = (int)round_up(b_glob, p.var_col ? kRowPad : kColPad);
     p.jt = kTileFloats / dp;                                   // 128 .. 8
     if (p.jt > 32) p.jt = 32;
-    p.n_rb_fwd = p.bl_pad / p.fwd_rows;
-    // small problems (BASELINE cfg 1 / 2: B = 3 / 64): 4-column tiles, so that row blocks x tiles still gives every SM a CTA
     p.small = !p.var_col && (int64_t)p.n_rb_fwd * (p.bg_pad / p.jt) < sms;
-    if (p.small) { p.jt = kSmallTile; if (p.fwd_lpr8) { p.fwd_lpr8 = 0; p.fwd_rows = kFwdWarps * (32 / p.dpt); p.n_rb_fwd = p.bl_pad / p.fwd_rows; } }
-    choose_splits(p.n_rb_fwd, sms * 3, p.bg_pad, p.jt, 4, p.n_js_fwd, p.js_len_fwd);   // 3 resident CTAs per SM
+    if (p.small) p.jt = kSmallTile;
+    else if (!p.var_col && dp <= 128 && fwd_map_tuning() == 0) set_map(dp / 16, 4);
+    const int fwd_res = fwd_wave_tuning() > 0 ? fwd_wave_tuning() : 3;   // CTAs per SM the balanced grid is sized in waves of
+    choose_splits(p.n_rb_fwd, sms * 3, p.bg_pad, p.jt, 4, p.n_js_fwd, p.js_len_fwd);
     p.tiles_fwd = p.bg_pad / p.jt;
-    p.seg_fwd = plan_segments(p.n_rb_fwd, p.tiles_fwd, sms * 3, fwd_seg_target() > 0 ? fwd_seg_target() : 21);
+    p.seg_fwd = plan_segments(p.n_rb_fwd, p.tiles_fwd, sms * fwd_res, fwd_seg_target() > 0 ? fwd_seg_target() : 21);
     p.slots_fwd = (p.tiles_fwd - 1) / p.seg_fwd.base + 2;
     if (p.slots_fwd > kMaxSplits) p.slots_fwd = kMaxSplits;
     // ---- fused backward sweep: its launcher plans the column split for the CTA shape it runs (<= kMaxSplits)

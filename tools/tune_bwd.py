@@ -19,7 +19,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--rows", type=int, default=0, help="rows of this shard (default: the whole batch); emulates one rank of a row-sharded job")
     ap.add_argument("--fwd-seg", default="", help="comma list of forward segment-length targets (column tiles per CTA)")
-    ap.add_argument("--fwd-lpr8", default="", help="comma list: 0 = shipped forward mapping, 1 / 2 = 8 lanes per row x 16 dims per lane with 4 / 5 CTAs per SM")
+    ap.add_argument("--fwd-wave", default="", help="comma list: CTAs per SM the forward grid is sized for (0 = as resident)")
+    ap.add_argument("--fwd-map", default="", help="comma list: 0 = shipped forward mapping (16 dims per lane for D <= 128), 1 = 32 dims per lane everywhere")
     ap.add_argument("--seg", default="0", help="comma list of segment-length targets (column tiles per CTA; 0 = default)")
     args = ap.parse_args()
     lib = _lib.load()
@@ -65,48 +66,32 @@ def main():
         print(f"variant {v:2d} seg {seg:3d}: backward total {ts[len(ts)//2]:.3f} ms (min {ts[0]:.3f})  max rel diff vs first {err:.1e}")
     lib.tcelbo_set_tuning(b"bwd_variant", 0)
     lib.tcelbo_set_tuning(b"bwd_seg_tiles", 0)
-    # forward sweep: segment-length targets
-    ref = None
-    for seg in [int(y) for y in args.fwd_seg.split(",") if y]:
-        _lib.check(lib.tcelbo_set_tuning(b"fwd_seg_tiles", seg), "set_tuning")
-        for _ in range(2):
-            out = torch.ops.tcelbo.tc_forward(z, mu, lv, 0, N, flags)
-        ts = []
-        for _ in range(args.reps):
-            flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = torch.ops.tcelbo.tc_forward(z, mu, lv, 0, N, flags)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        if ref is None:
-            ref = [t.clone() for t in out[:2]]
-        err = max(((a - b).abs().max() / b.abs().max()).item() for a, b in zip(out[:2], ref))
-        ts.sort()
-        print(f"forward seg {seg:3d}: forward total {ts[len(ts)//2]:.3f} ms (min {ts[0]:.3f})  max rel diff vs first {err:.1e}")
-    lib.tcelbo_set_tuning(b"fwd_seg_tiles", 0)
-    ref = None
-    for v in [int(y) for y in args.fwd_lpr8.split(",") if y]:
-        _lib.check(lib.tcelbo_set_tuning(b"fwd_lpr8", v), "set_tuning")
-        for _ in range(2):
-            out = torch.ops.tcelbo.tc_forward(z, mu, lv, 0, N, flags)
-        ts = []
-        for _ in range(args.reps):
-            flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = torch.ops.tcelbo.tc_forward(z, mu, lv, 0, N, flags)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        if ref is None:
-            ref = [t.clone() for t in out[:2]]
-        err = max(((a - b).abs().max() / b.abs().max()).item() for a, b in zip(out[:2], ref))
-        ts.sort()
-        print(f"forward lpr8 {v}: forward total {ts[len(ts)//2]:.3f} ms (min {ts[0]:.3f})  max rel diff vs first {err:.1e}")
-    lib.tcelbo_set_tuning(b"fwd_lpr8", 0)
+    # forward sweep: segment-length targets, lane mapping, grid wave size
+    def sweep_fwd(key, label, values):
+        ref = None
+        for v in values:
+            _lib.check(lib.tcelbo_set_tuning(key, v), "set_tuning")
+            for _ in range(2):
+                out = torch.ops.tcelbo.tc_forward(z, mu, lv, 0, N, flags)
+            ts = []
+            for _ in range(args.reps):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = torch.ops.tcelbo.tc_forward(z, mu, lv, 0, N, flags)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            if ref is None:
+                ref = [t.clone() for t in out[:2]]
+            err = max(((a - b).abs().max() / b.abs().max()).item() for a, b in zip(out[:2], ref))
+            ts.sort()
+            print(f"forward {label} {v:3d}: forward total {ts[len(ts)//2]:.3f} ms (min {ts[0]:.3f})  max rel diff vs first {err:.1e}")
+        lib.tcelbo_set_tuning(key, 0)
 
+    sweep_fwd(b"fwd_seg_tiles", "seg", [int(y) for y in args.fwd_seg.split(",") if y])
+    sweep_fwd(b"fwd_map", "map", [int(y) for y in args.fwd_map.split(",") if y])
+    sweep_fwd(b"fwd_wave", "wave", [int(y) for y in args.fwd_wave.split(",") if y])
 
 if __name__ == "__main__":
     main()
