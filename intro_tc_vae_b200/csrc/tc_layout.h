@@ -111,7 +111,7 @@ inline Segments plan_segments(int64_t n_blocks, int tiles_per_block, int slots, 
 
 inline int& fwd_seg_target() { static int v = 0; return v; }    // tuning: forward segment length in column tiles (0 = default)
 inline int& fwd_map_tuning() { static int v = 0; return v; }    // tools/tune_bwd.py --fwd-map: 1 = 32 dims per lane everywhere (round-1 mapping)
-inline int& fwd_wave_tuning() { static int v = 0; return v; }   // tuning: CTAs per SM the forward grid is sized for (0 = 3)
+inline int& fwd_wave_tuning() { static int v = 0; return v; }   // tuning: CTAs per SM the forward grid is sized for (0 = as resident: 4 / 3)
 
 // `sms` = multiprocessor count of the current device (148 on B200).
 inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int sms) {
@@ -143,7 +143,7 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.small = !p.var_col && (int64_t)p.n_rb_fwd * (p.bg_pad / p.jt) < sms;
     if (p.small) p.jt = kSmallTile;
     else if (!p.var_col && dp <= 128 && fwd_map_tuning() == 0) set_map(dp / 16, 4);
-    const int fwd_res = fwd_wave_tuning() > 0 ? fwd_wave_tuning() : 3;   // CTAs per SM the balanced grid is sized in waves of
+    const int fwd_res = fwd_wave_tuning() > 0 ? fwd_wave_tuning() : (p.fwd_kch == 4 ? 4 : 3);   // resident CTAs per SM: wave size
     choose_splits(p.n_rb_fwd, sms * 3, p.bg_pad, p.jt, 4, p.n_js_fwd, p.js_len_fwd);
     p.tiles_fwd = p.bg_pad / p.jt;
     p.seg_fwd = plan_segments(p.n_rb_fwd, p.tiles_fwd, sms * fwd_res, fwd_seg_target() > 0 ? fwd_seg_target() : 21);

@@ -214,3 +214,84 @@ class GraphedKLLoss:
             if self.mode == "autograd":
                 self.dmu, self.dlogvar = self.mu.grad, self.logvar.grad
         return self.loss, self.dmu, self.dlogvar
+
+
+class HostPipeline:
+    """Streams HOST-resident batches through a loss step: host -> device copy, step, device -> host copy on three streams,
+    ``depth``-deep, so that the PCIe transfers of neighbouring batches hide behind the kernels of the current one.
+
+    ``step_fn(mu, logvar, eps) -> (loss, dmu, dlogvar)`` runs on the current stream on ``[b_loc, d]`` device tensors that stay
+    valid until it returns (a :class:`GraphedKLLoss` instance is such a callable; so is an eager function that builds leaves
+    from its arguments, calls ``compute_kl_loss`` and ``backward()``).  ``submit`` only enqueues work and returns the batch's
+    sequence number; the pinned host outputs handed to it are complete after ``wait(seq)`` (or ``drain()``), and the pinned
+    host inputs may be reused once ``inputs_consumed(seq)`` is true (always the case after ``wait(seq)``).
+    """
+
+    def __init__(self, step_fn, b_loc: int, d: int, device, depth: int = 2):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.step_fn = step_fn
+        self.device = torch.device(device)
+        self.depth = int(depth)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self._in = [[torch.empty(b_loc, d, **f32) for _ in range(3)] for _ in range(depth)]
+        self._out = [[torch.empty((), **f32), torch.empty(b_loc, d, **f32), torch.empty(b_loc, d, **f32)] for _ in range(depth)]
+        ev = lambda: [torch.cuda.Event() for _ in range(depth)]
+        self._in_ready, self._in_free, self._out_ready, self._out_done = ev(), ev(), ev(), ev()
+        self.s_in = torch.cuda.Stream(self.device)
+        self.s_out = torch.cuda.Stream(self.device)
+        self.seq = 0
+        torch.cuda.synchronize(self.device)
+
+    def begin(self) -> None:
+        """Order the copy streams after what the current stream has been given so far (e.g. a timing event)."""
+        cur = torch.cuda.current_stream(self.device)
+        self.s_in.wait_stream(cur)
+        self.s_out.wait_stream(cur)
+
+    def submit(self, mu_h: Tensor, logvar_h: Tensor, eps_h: Tensor, loss_h: Tensor, dmu_h: Tensor, dlogvar_h: Tensor) -> int:
+        k, slot = self.seq, self.seq % self.depth
+        cur = torch.cuda.current_stream(self.device)
+        with torch.no_grad():
+            with torch.cuda.stream(self.s_in):
+                if k >= self.depth:
+                    self.s_in.wait_event(self._in_free[slot])          # the step that last read this slot has been issued its reads
+                for dst, src in zip(self._in[slot], (mu_h, logvar_h, eps_h)):
+                    dst.copy_(src, non_blocking=True)
+                self._in_ready[slot].record(self.s_in)
+            cur.wait_event(self._in_ready[slot])
+            loss, dmu, dlogvar = self.step_fn(*self._in[slot])
+            self._in_free[slot].record(cur)
+            if k >= self.depth:
+                cur.wait_event(self._out_done[slot])                    # the device -> host copy that last read this slot
+            o = self._out[slot]
+            o[0].copy_(loss.detach().reshape(()))
+            o[1].copy_(dmu)
+            o[2].copy_(dlogvar)
+            self._out_ready[slot].record(cur)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self._out_ready[slot])
+                loss_h.copy_(o[0].reshape(loss_h.shape), non_blocking=True)
+                dmu_h.copy_(o[1], non_blocking=True)
+                dlogvar_h.copy_(o[2], non_blocking=True)
+                self._out_done[slot].record(self.s_out)
+        self.seq += 1
+        return k
+
+    def inputs_consumed(self, seq: int) -> bool:
+        if seq >= self.seq:
+            raise ValueError(f"batch {seq} has not been submitted")
+        return self._in_free[seq % self.depth].query()                  # a later batch in the same slot only makes this conservative
+
+    def wait(self, seq: int) -> None:
+        """Block the host until batch ``seq``'s outputs are in its host buffers."""
+        if seq >= self.seq:
+            raise ValueError(f"batch {seq} has not been submitted")
+        self._out_done[seq % self.depth].synchronize()                  # stream order: a later batch's copy implies this one's
+
+    def fence(self) -> None:
+        """Make the current stream wait for every device -> host copy submitted so far."""
+        torch.cuda.current_stream(self.device).wait_stream(self.s_out)
+
+    def drain(self) -> None:
+        self.s_out.synchronize()

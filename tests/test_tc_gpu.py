@@ -533,6 +533,45 @@ def test_graphed_step_matches_eager_autograd_and_oracle(B, D, family, estimator)
             assert relerr(dlv, lv_o.grad) < GRAD_RTOL
 
 
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_host_pipeline_streams_distinct_batches(depth):
+    """graphs.HostPipeline: 7 DIFFERENT host batches streamed through a graphed step and through an eager step (copies on side
+    streams, `depth` batches in flight) give, batch by batch, what the step gives when called on its own."""
+    from intro_tc_vae_b200.graphs import GraphedKLLoss, HostPipeline
+    ops = _ops()
+    B, D, N, beta = 320, 128, 16704, 0.5
+    dev = torch.device("cuda:0")
+    graphed = GraphedKLLoss(B, D, N, beta, dev)
+
+    def eager_fn(mu_s, lv_s, eps_s):
+        with torch.enable_grad():
+            mu_d, lv_d = mu_s.detach().requires_grad_(True), lv_s.detach().requires_grad_(True)
+            loss = ops.kl_tc_loss_mean(ops.reparameterize(mu_d, lv_d, eps_s), mu_d, lv_d, N, beta, "mss")[0]
+            loss.backward()
+        return loss, mu_d.grad, lv_d.grad
+
+    batches = [[t.pin_memory() for t in _random_latents(B, D, "base" if k % 2 else "sharp", seed=300 + k)] for k in range(7)]
+    want = []
+    for mu_h, lv_h, eps_h in batches:
+        want.append([t.clone().cpu() for t in graphed(mu_h, lv_h, eps_h)])
+    for fn in (graphed, eager_fn):
+        pipe = HostPipeline(fn, B, D, dev, depth=depth)
+        outs = [(torch.empty(1).pin_memory(), torch.empty(B, D).pin_memory(), torch.empty(B, D).pin_memory()) for _ in batches]
+        seqs = [pipe.submit(*b, *o) for b, o in zip(batches, outs)]
+        assert seqs == list(range(7))
+        pipe.wait(3)
+        assert pipe.inputs_consumed(3)
+        for k in range(4):                                           # stream order: everything up to batch 3 has landed
+            assert relerr(outs[k][0], want[k][0].reshape(1)) < 2e-6
+        pipe.drain()
+        for k in range(7):
+            assert relerr(outs[k][0], want[k][0].reshape(1)) < 2e-6
+            assert relerr(outs[k][1], want[k][1]) < 1e-5
+            assert relerr(outs[k][2], want[k][2]) < 1e-5
+        with pytest.raises(ValueError):
+            pipe.wait(7)
+
+
 @pytest.mark.parametrize("B,D,parts,family", [(256, 128, 2, "base"), (384, 64, 4, "sharp"), (296, 20, 8, "base"), (512, 256, 2, "base")])
 def test_peer_exchange_entry_points_emulated_on_one_gpu(B, D, parts, family):
     """tcelbo_klloss_forward_peer / _backward_peer take plain device pointer tables, so P ranks can be played one after the

@@ -1,10 +1,8 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-T=r2r
-timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/${T}_pytest.log 2>&1; tail -5 gpurun_out/${T}_pytest.log
-timeout 300 python tools/tune_bwd.py --variants=0 --reps 7 --fwd-map 1,0 --fwd-wave 3,4,0 --fwd-seg 16,21,32 > gpurun_out/${T}_tune_128.log 2>&1; cat gpurun_out/${T}_tune_128.log
-timeout 300 python tools/tune_bwd.py --variants=0 --reps 7 --rows 1024 --fwd-map 1,0 --fwd-wave 3,4 > gpurun_out/${T}_tune_128_r1024.log 2>&1; cat gpurun_out/${T}_tune_128_r1024.log
-timeout 300 python tools/tune_bwd.py --variants=0 --reps 7 --batch 4096 --zdim 64 --fwd-map 1,0 > gpurun_out/${T}_tune_64.log 2>&1; cat gpurun_out/${T}_tune_64.log
-timeout 300 python tools/tune_bwd.py --variants=0 --reps 7 --batch 4000 --zdim 20 --fwd-map 1,0 > gpurun_out/${T}_tune_20.log 2>&1; cat gpurun_out/${T}_tune_20.log
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench_n1.err; cat gpurun_out/${T}_bench_n1.json; tail -3 gpurun_out/${T}_bench_n1.err
+T=r2t
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench_n1.err; cat gpurun_out/${T}_bench_n1.json | cut -c1-400; tail -3 gpurun_out/${T}_bench_n1.err
+timeout 300 python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-train > gpurun_out/${T}_bench_nograph.json 2> gpurun_out/${T}_bench_nograph.err && \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_fwd_kernel|tc_bwd_ds_kernel" --launch-skip 8 --launch-count 2 -f -o gpurun_out/${T}_full python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-train > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log | cut -c1-300
+ls -la gpurun_out/${T}_full.ncu-rep
