@@ -68,8 +68,10 @@ __device__ __forceinline__ float ds_column(float mu, const float* __restrict__ g
         const u64 q2 = ffma2(dl2, dl2, nk2);                                               // q' = q - 1/(2 ln2)
         float q0, q1;
         unpack2(q2, q0, q1);
-        const float c0 = fmin_nan(q0, qmx[2 * p]), c1 = fmin_nan(q1, qmx[2 * p + 1]);
-        u64 e2 = pack2(ex2(-c0), ex2(-c1));
+        // A clamped pair contributes r = 0 whatever its weight, so the exponent needs no min(q, qmax) here (the forward's clamp
+        // decides the VALUE of a clamped term; the backward only needs to know that it was clamped): 2 ALU instructions less
+        // per pair of log-densities, 3.42 -> 3.11 ms at 8192 x 8192 x 128.
+        u64 e2 = pack2(ex2(-q0), ex2(-q1));
         if (kSpecial) {
             float r0, r1, l2;
             weight_of(w, i_glob0 + 2 * p, j, r0, l2);
@@ -87,7 +89,7 @@ __device__ __forceinline__ float ds_column(float mu, const float* __restrict__ g
         }
         const u64 t2 = fmul2(r2, dl2);
         A2[p] = fadd2(A2[p], t2);
-        CR2[p] = ffma2(r2, pack2(c0, c1), CR2[p]);
+        CR2[p] = ffma2(r2, q2, CR2[p]);
         if (p & 1) Gb = ffma2(t2, ns2[p], Gb); else Ga = ffma2(t2, ns2[p], Ga);
     }
     float lo, hi;
@@ -558,6 +560,8 @@ static cudaError_t launch_bwd_ds(const Plan& p, const BwdFusedArgs& a, BwdFinArg
             case 2:  return launch_bwd_ds_t<5, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);    // 10 rows/warp, 16 warps/SM
             case 3:  return launch_bwd_ds_t<8, 4, 12, 1, 16, 8>(p, a, fin, st);                // shipped shape, clamp mask by multiply
             case 4:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 4, true>(p, a, fin, st);           // two columns in lockstep
+            case 5:  return launch_bwd_ds_t<8, 4, 16, 1, 16, 8, false, true>(p, a, fin, st);   // 16 rows/warp, 16 warps/SM (128 regs)
+            case 6:  return launch_bwd_ds_t<7, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);    // 14 rows/warp, 16 warps/SM
             default: return launch_bwd_ds_t<8, 4, 12, 1, 16, 8, false, true>(p, a, fin, st);   // 16 rows/warp, 12 warps/SM (168 regs),
         }                                                                                       // 8 columns per basic block, mask by select
     }
