@@ -116,10 +116,8 @@ __device__ __forceinline__ void ds_column_x2(float mu_a, float mu_b, const float
         const u64 qb2 = ffma2(dlb2, dlb2, nk2);
         float qa0, qa1, qb0, qb1;
         unpack2(qa2, qa0, qa1); unpack2(qb2, qb0, qb1);
-        const float ca0 = fmin_nan(qa0, qmx[2 * p]), ca1 = fmin_nan(qa1, qmx[2 * p + 1]);
-        const float cb0 = fmin_nan(qb0, qmx[2 * p]), cb1 = fmin_nan(qb1, qmx[2 * p + 1]);
-        const u64 ea2 = pack2(ex2(-ca0), ex2(-ca1));
-        const u64 eb2 = pack2(ex2(-cb0), ex2(-cb1));
+        const u64 ea2 = pack2(ex2(-qa0), ex2(-qa1));
+        const u64 eb2 = pack2(ex2(-qb0), ex2(-qb1));
         const u64 ma2 = pack2(fset_le_ds(qa0, qmx[2 * p]), fset_le_ds(qa1, qmx[2 * p + 1]));
         const u64 mb2 = pack2(fset_le_ds(qb0, qmx[2 * p]), fset_le_ds(qb1, qmx[2 * p + 1]));
         const u64 ra2 = fmul2(ffma2(ea2, gps2[p], gqa2), ma2);
@@ -127,7 +125,7 @@ __device__ __forceinline__ void ds_column_x2(float mu_a, float mu_b, const float
         const u64 ta2 = fmul2(ra2, dla2);
         const u64 tb2 = fmul2(rb2, dlb2);
         A2[p] = fadd2(A2[p], fadd2(ta2, tb2));
-        CR2[p] = ffma2(rb2, pack2(cb0, cb1), ffma2(ra2, pack2(ca0, ca1), CR2[p]));
+        CR2[p] = ffma2(rb2, qb2, ffma2(ra2, qa2, CR2[p]));
         Ga = ffma2(ta2, ns2[p], Ga);
         Gb = ffma2(tb2, ns2[p], Gb);
     }
@@ -136,8 +134,8 @@ __device__ __forceinline__ void ds_column_x2(float mu_a, float mu_b, const float
     unpack2(Gb, lo, hi); g_b = lo + hi;
 }
 
-// UNR: columns per basic block; X2: two columns in lockstep; MSEL: clamp mask by select (ALU pipe) instead of a packed multiply
-template <int RP, int CH, int NW, int MINB, int JT, int UNR, bool X2, bool MSEL>
+// UNR: columns per basic block; X2: 1 = two columns in lockstep; MSEL: clamp mask by select (ALU pipe) instead of a packed multiply
+template <int RP, int CH, int NW, int MINB, int JT, int UNR, int X2, bool MSEL>
 __global__ void __launch_bounds__(NW * 32, MINB)
 tc_bwd_ds_kernel(const __grid_constant__ BwdDsArgs a) {
     constexpr int RW = 2 * RP;                                               // rows per warp
@@ -290,7 +288,7 @@ tc_bwd_ds_kernel(const __grid_constant__ BwdDsArgs a) {
                 red_add_f32(gptr, g);
                 gptr += pitch;
             }
-        } else if (X2) {
+        } else if (X2 == 1) {
 #pragma unroll(UNR / 2)
             for (int jj = 0; jj < JT; jj += 2) {
                 float ga, gb;
@@ -346,7 +344,7 @@ static bool make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64
 static int g_ds_seg_target = 0;
 void set_bwd_seg_target(int v) { g_ds_seg_target = v; }
 
-template <int RP, int CH, int NW, int MINB, int JT, int UNR = 8, bool X2 = false, bool MSEL = false>
+template <int RP, int CH, int NW, int MINB, int JT, int UNR = 8, int X2 = 0, bool MSEL = false>
 static cudaError_t launch_bwd_ds_t(const Plan& p, const BwdFusedArgs& u, BwdFinArgs* fin, cudaStream_t st) {
     constexpr int ROWS = (NW / CH) * 2 * RP, DPS = 32 * CH;
     const size_t smem = ((size_t)kStages * JT * DPS + (size_t)kStages * ROWS * JT + (size_t)NW * JT * 2 * RP + (size_t)NW * 2 * RP * 2) * sizeof(float)
@@ -559,9 +557,7 @@ static cudaError_t launch_bwd_ds(const Plan& p, const BwdFusedArgs& a, BwdFinArg
             case 1:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);    // 12 rows/warp, 16 warps/SM (128 regs)
             case 2:  return launch_bwd_ds_t<5, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);    // 10 rows/warp, 16 warps/SM
             case 3:  return launch_bwd_ds_t<8, 4, 12, 1, 16, 8>(p, a, fin, st);                // shipped shape, clamp mask by multiply
-            case 4:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 4, true>(p, a, fin, st);           // two columns in lockstep
-            case 5:  return launch_bwd_ds_t<8, 4, 16, 1, 16, 8, false, true>(p, a, fin, st);   // 16 rows/warp, 16 warps/SM (128 regs)
-            case 6:  return launch_bwd_ds_t<7, 4, 8, 2, 16, 8, false, true>(p, a, fin, st);    // 14 rows/warp, 16 warps/SM
+            case 4:  return launch_bwd_ds_t<6, 4, 8, 2, 16, 4, 1>(p, a, fin, st);              // two columns in lockstep
             default: return launch_bwd_ds_t<8, 4, 12, 1, 16, 8, false, true>(p, a, fin, st);   // 16 rows/warp, 12 warps/SM (168 regs),
         }                                                                                       // 8 columns per basic block, mask by select
     }

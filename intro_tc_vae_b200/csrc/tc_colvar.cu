@@ -328,8 +328,7 @@ tc_bwd_colvar_kernel(const BwdFusedArgs a) {
                         const float dl = fmaf(zr[r][e], sj[e], nm[e]);
                         const float q = dl * dl;
                         const float tt = c2[e] - q;
-                        const float tcl = fmax_nan(tt, -kK50);
-                        float ev = ex2(tcl);
+                        float ev = ex2(tt);                            // no clamp needed: a clamped pair is masked below
                         if (special) ev *= rho;
                         const float coef = fmaf(ev, gps[r][e], g);
                         const float rr = (tt < -kK50) ? 0.0f : coef;

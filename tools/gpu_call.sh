@@ -1,7 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-T=r2u
-timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/${T}_pytest.log 2>&1; tail -5 gpurun_out/${T}_pytest.log
-timeout 300 python tools/tune_bwd.py --variants=0,1,2,3,4,5,6 --reps 7 > gpurun_out/${T}_tune.log 2>&1; cat gpurun_out/${T}_tune.log
-timeout 300 python tools/tune_bwd.py --variants=0,1,2,5,6 --reps 7 --rows 1024 > gpurun_out/${T}_tune_r1024.log 2>&1; cat gpurun_out/${T}_tune_r1024.log
+T=r2x
+timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/${T}_pytest.log 2>&1; tail -3 gpurun_out/${T}_pytest.log
+timeout 300 python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-train > gpurun_out/${T}_bench_nograph.json 2> gpurun_out/${T}_bench_nograph.err && \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_fwd_kernel|tc_bwd_ds_kernel" --launch-skip 8 --launch-count 2 -f -o gpurun_out/${T}_full python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-train > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log | cut -c1-200
