@@ -41,7 +41,7 @@ def main():
     out = ["# Round 2: launch lists, full ncu capture and bench lines of the shipped build (one B200, 1965 MHz)\n",
            "Workload: `bench.py` step = `compute_kl_loss`-equivalent evaluation (reparameterize + KL + TC(MSS) + mean + backward to mu / logvar) at "
            "global batch 8192, z_dim 128, N = 16 704; 6 library launches (`tcelbo_klloss_forward_ex` / `_backward_ex`).\n",
-           "## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none -c 600`, `bench.py --steps 3 --warmup 3 --no-graph "
+           "## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none -c 700`, `bench.py --steps 3 --warmup 3 --no-graph "
            "--no-cpu-baseline --no-train`; file `r2_launches.csv`)\n",
            "`--no-graph` issues the same C-ABI step the graph replays (`GraphedKLLoss(capture=False)`); the capture also contains bench.py's "
            "eager drop-in steps (`reparam_*`, the `at::` fill / add kernels of autograd), its L2 flush (`FillFunctor<unsigned char>`) and the ex2 probe.\n"]
