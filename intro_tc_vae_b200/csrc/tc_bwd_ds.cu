@@ -138,6 +138,7 @@ __device__ __forceinline__ void ds_column_x2(float mu_a, float mu_b, const float
 template <int RP, int CH, int NW, int MINB, int JT, int UNR, int X2, bool MSEL>
 __global__ void __launch_bounds__(NW * 32, MINB)
 tc_bwd_ds_kernel(const __grid_constant__ BwdDsArgs a) {
+    pdl_trigger(); pdl_wait();                               // programmatic dependent launch, tc_common.cuh
     constexpr int RW = 2 * RP;                                               // rows per warp
     constexpr int NRG = NW / CH;                                             // row groups per CTA
     constexpr int ROWS = NRG * RW;
@@ -374,13 +375,13 @@ static cudaError_t launch_bwd_ds_t(const Plan& p, const BwdFusedArgs& u, BwdFinA
     a.b_loc = u.b_loc; a.bl_pad = u.bl_pad; a.bg_pad = u.bg_pad; a.row_offset = u.row_offset; a.pitch = p.dp;
     a.seg = seg; a.n_rb = n_rb; a.w = u.w;
     LaunchScope scope(kKernBwdRow, st);
-    kern<<<seg.n_ctas, NW * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(seg.n_ctas), dim3(NW * 32), smem, st, a);
 }
 
 // Elementwise over [B,D]: sum the column-split partials of the row-local sums (8 independent loads in flight), scale,
 // and add the fused KL gradient when asked (ops.py:161-163).
 __global__ void bwd_fused_finalize_kernel(const BwdFinArgs a) {
+    pdl_trigger(); pdl_wait();                               // programmatic dependent launch, tc_common.cuh
     const int64_t n_row = (int64_t)a.b_loc * a.d;
     const int64_t n_col = a.scratch_parts != nullptr ? 0 : (int64_t)a.b_glob * a.d;
     const size_t split_stride = (size_t)a.bl_pad * a.dp;
@@ -463,6 +464,7 @@ __device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_floa
 // 16-byte aligned; bwd_fused_finalize_kernel covers the rest.  At one rank of eight the step spends as long in its small kernels
 // as in 5 % of its sweeps, so their memory-level parallelism matters there.
 __global__ void bwd_fused_finalize_v4_kernel(const BwdFinArgs a) {
+    pdl_trigger(); pdl_wait();                               // programmatic dependent launch, tc_common.cuh
     const int d4 = a.d / 4;
     const int64_t n_row = (int64_t)a.b_loc * d4;
     const int64_t n_col = a.scratch_parts != nullptr ? 0 : (int64_t)a.b_glob * d4;
@@ -580,9 +582,7 @@ cudaError_t launch_bwd_fused_finalize(const Plan& p, const BwdFinArgs& a, cudaSt
     const int64_t n = ((int64_t)p.b_loc * p.d + (int64_t)p.b_glob * p.d) / (vec ? 4 : 1);
     int64_t g = (n + 255) / 256; if (g > 148 * 16) g = 148 * 16; if (g < 1) g = 1;
     LaunchScope scope(kKernNone, st);
-    if (vec) bwd_fused_finalize_v4_kernel<<<(int)g, 256, 0, st>>>(a);
-    else     bwd_fused_finalize_kernel<<<(int)g, 256, 0, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(vec ? bwd_fused_finalize_v4_kernel : bwd_fused_finalize_kernel, dim3((int)g), dim3(256), 0, st, a);
 }
 
 }  // namespace tcelbo

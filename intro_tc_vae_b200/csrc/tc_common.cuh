@@ -7,6 +7,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
+#include <utility>
 
 namespace tcelbo {
 
@@ -150,6 +152,33 @@ __device__ __forceinline__ void peer_barrier(const PeerSync& ps) {
         } while ((int)(v - want) < 0);
     }
     __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the step starts with `pdl_trigger(); pdl_wait();`: the trigger lets the NEXT
+// kernel of the stream be dispatched as soon as all CTAs of this one are running (its CTAs become resident as slots free up and
+// block in their own wait), the wait returns once the PREVIOUS kernel has completed and its writes are visible.  What is saved
+// is the launch latency at each of the step's kernel boundaries -- a fixed cost that matters for small shards (N = 8: 1024
+// rows per GPU) and for the reference's training batch (B = 64).  Without the launch attribute both instructions are no-ops.
+// TCELBO_PDL=0 launches everything fully serialised.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = std::getenv("TCELBO_PDL"); return e == nullptr || std::atoi(e) != 0; }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 // online logsumexp in base 2: (m, s) <- (m, s) (+) 2^x

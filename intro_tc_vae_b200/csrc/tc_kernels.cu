@@ -22,6 +22,7 @@ namespace tcelbo {
 // Peer exchange, forward: copy this rank's rows of mu into its peer-mapped buffer and open the next forward barrier
 // (the prologue kernel that follows on the stream signals and waits on that number, tc_common.cuh: PeerSync).
 __global__ void publish_kernel(const float* __restrict__ src, int64_t ld, int b_loc, int d, float* __restrict__ dst, unsigned int* epoch) {
+    pdl_trigger(); pdl_wait();                               // programmatic dependent launch, tc_common.cuh
     if (blockIdx.x == 0 && threadIdx.x == 0 && epoch != nullptr) atomicAdd(epoch, 1u);
     const int64_t n = (int64_t)b_loc * d;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x)
@@ -30,6 +31,7 @@ __global__ void publish_kernel(const float* __restrict__ src, int64_t ld, int b_
 
 template <bool kParts>
 __global__ void prep_scalar_kernel(const PrepArgs a) {
+    pdl_trigger(); pdl_wait();                               // programmatic dependent launch, tc_common.cuh
     const int64_t n_col = (int64_t)a.bg_pad * a.dp, n_row = (int64_t)a.bl_pad * a.dp;
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket = 0u;
     // ---- rows first (local data only): per-(i,d) constants, optionally the fused reparameterize
@@ -87,6 +89,7 @@ __device__ __forceinline__ float4 ld_volatile_v4(const float* p) {          // p
 // (the encoder's chunk views and dense tensors both are, for D % 4 == 0); prep_scalar_kernel covers the rest.
 template <bool kParts>
 __global__ void prep_kernel(const PrepArgs a) {
+    pdl_trigger(); pdl_wait();                               // programmatic dependent launch, tc_common.cuh
     const int dp4 = a.dp / 4;
     const int64_t n_col = (int64_t)a.bg_pad * dp4, n_row = (int64_t)a.bl_pad * dp4;
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket = 0u;
@@ -233,6 +236,7 @@ __device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt,
 template <int LPR, int JTS, int KCH = 8, int MINB = 3>
 __global__ void __launch_bounds__(kFwdWarps * 32, MINB)
 tc_fwd_kernel(const FwdArgs a) {
+    pdl_trigger(); pdl_wait();                               // programmatic dependent launch, tc_common.cuh
     constexpr int DP = 4 * KCH * LPR;
     constexpr int RPW = 32 / LPR;
     constexpr int ROWS = kFwdWarps * RPW;
@@ -342,6 +346,7 @@ tc_fwd_kernel(const FwdArgs a) {
 // One warp per row: sum the column-split partials (float4 per lane, 8 independent loads in flight), take logs,
 // emit log_qz / log_qz_prod and, when asked, the fused KL and (beta-1)*TC + KL of solvers/tc.py:83-89.
 __global__ void fwd_finalize_kernel(const FinArgs a) {
+    pdl_trigger(); pdl_wait();                               // programmatic dependent launch, tc_common.cuh
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row_raw = blockIdx.x * (blockDim.x >> 5) + warp;
     const bool row_ok = row_raw < a.b_loc;
@@ -458,6 +463,7 @@ __global__ void fwd_finalize_kernel(const FinArgs a) {
 __global__ void bwd_prep_kernel(const BwdUpstream u, const float* __restrict__ S, int b_loc, int bl_pad, int dp,
                                 float* __restrict__ gps, float* __restrict__ gj, float* __restrict__ gk,
                                 float* __restrict__ zero, int64_t zero_n) {
+    pdl_trigger(); pdl_wait();                               // programmatic dependent launch, tc_common.cuh
     const int64_t n = (int64_t)bl_pad * dp;
     const float inv_b = 1.0f / (float)b_loc;
     const float gl_mean = u.g_loss_mean ? u.g_loss_mean[0] * inv_b : 0.0f;
@@ -524,14 +530,12 @@ static cudaError_t launch_fwd_t(const Plan& p, const FwdArgs& a, cudaStream_t st
         configured = 1;
     }
     LaunchScope scope(kKernFwd, st);
-    tc_fwd_kernel<LPR, JTS, KCH, MINB><<<p.seg_fwd.n_ctas, kFwdWarps * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(tc_fwd_kernel<LPR, JTS, KCH, MINB>, dim3(p.seg_fwd.n_ctas), dim3(kFwdWarps * 32), smem, st, a);
 }
 
 cudaError_t launch_publish(const float* src, int64_t ld, int b_loc, int d, float* dst, unsigned int* epoch, cudaStream_t st) {
     LaunchScope scope(kKernNone, st);
-    publish_kernel<<<grid_for((int64_t)b_loc * d, 256, 148 * 4), 256, 0, st>>>(src, ld, b_loc, d, dst, epoch);
-    return cudaGetLastError();
+    return launch_pdl(publish_kernel, dim3(grid_for((int64_t)b_loc * d, 256, 148 * 4)), dim3(256), 0, st, src, ld, b_loc, d, dst, epoch);
 }
 
 static inline bool aligned16(const void* p, int64_t ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ld % 4 == 0); }
@@ -541,16 +545,17 @@ cudaError_t launch_prep(const PrepArgs& a, cudaStream_t st) {
                      && aligned16(a.mu_loc, a.ldmu_loc) && aligned16(a.z_out, a.ldz_out) && aligned16(a.logvar, a.ldlv)
                      && (a.parts == nullptr || a.ld_part % 4 == 0);          // the ranks' published buffers are dense, 16-byte aligned allocations
     LaunchScope scope(kKernNone, st);
+    cudaError_t le;
     if (vec) {
         const int64_t n = (int64_t)(a.bg_pad > a.bl_pad ? a.bg_pad : a.bl_pad) * (a.dp / 4);
-        if (a.parts != nullptr) prep_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(a);
-        else                    prep_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(a);
+        if (a.parts != nullptr) le = launch_pdl(prep_kernel<true>, dim3(grid_for(n, 256)), dim3(256), 0, st, a);
+        else                    le = launch_pdl(prep_kernel<false>, dim3(grid_for(n, 256)), dim3(256), 0, st, a);
     } else {
         const int64_t n = (int64_t)(a.bg_pad > a.bl_pad ? a.bg_pad : a.bl_pad) * a.dp;
-        if (a.parts != nullptr) prep_scalar_kernel<true><<<grid_for(n, 256), 256, 0, st>>>(a);
-        else                    prep_scalar_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(a);
+        if (a.parts != nullptr) le = launch_pdl(prep_scalar_kernel<true>, dim3(grid_for(n, 256)), dim3(256), 0, st, a);
+        else                    le = launch_pdl(prep_scalar_kernel<false>, dim3(grid_for(n, 256)), dim3(256), 0, st, a);
     }
-    return cudaGetLastError();
+    return le;
 }
 
 cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st) {
@@ -584,8 +589,7 @@ cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st) {
 
 cudaError_t launch_fwd_finalize(const Plan& p, const FinArgs& a, cudaStream_t st) {
     LaunchScope scope(kKernNone, st);
-    fwd_finalize_kernel<<<p.n_fin_ctas, kFinWarps * 32, 0, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(fwd_finalize_kernel, dim3(p.n_fin_ctas), dim3(kFinWarps * 32), 0, st, a);
 }
 
 cudaError_t launch_bwd_prep(const Plan& p, const BwdUpstream& u, const float* S, float* gps, float* gj, float* gk,
@@ -593,8 +597,8 @@ cudaError_t launch_bwd_prep(const Plan& p, const BwdUpstream& u, const float* S,
     const int64_t n = (int64_t)p.bl_pad * p.dp;
     const int64_t total = (n > (int64_t)zero_n ? n : (int64_t)zero_n) / 4;        // one float4 per thread and pass
     LaunchScope scope(kKernNone, st);
-    bwd_prep_kernel<<<grid_for(total, 256), 256, 0, st>>>(u, S, p.b_loc, p.bl_pad, p.dp, gps, gj, gk, zero, (int64_t)zero_n);
-    return cudaGetLastError();
+    const cudaError_t le = launch_pdl(bwd_prep_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, u, S, p.b_loc, p.bl_pad, p.dp, gps, gj, gk, zero, (int64_t)zero_n);
+    return le;
 }
 
 }  // namespace tcelbo

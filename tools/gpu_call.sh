@@ -1,7 +1,11 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-T=r2z
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench_n1.err; cat gpurun_out/${T}_bench_n1.json | cut -c1-200; tail -3 gpurun_out/${T}_bench_n1.err
-timeout 300 python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-train > gpurun_out/${T}_bench_nograph.json 2> gpurun_out/${T}_bench_nograph.err && \
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-train > gpurun_out/${T}_ncu.log 2>&1; tail -1 gpurun_out/${T}_ncu.log | cut -c1-200
+T=r3b
+N=8
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${T}_bench_n$N.json 2> gpurun_out/${T}_bench_n$N.err
+tail -2 gpurun_out/${T}_bench_n$N.err
+python -c "
+import json;j=json.loads([l for l in open('gpurun_out/${T}_bench_n$N.json') if l.startswith('{')][-1])
+print($N, {k:j[k] for k in ('ms_per_step','value','gpu_launches')}, j['e2e']['ms_per_step'], j['e2e']['serial_ms_per_step'], j['dropin']['ms_per_step'], j['e2e_dropin']['ms_per_step'], j['roofline']['kernel_ms'], (j['train'] or {}).get('value'))
+"
