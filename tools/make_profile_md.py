@@ -63,6 +63,8 @@ def main():
     out.append("")
     out.append(open(P("r2_small_batch_notes.md")).read())
     out.append("## Bench lines (`bench.py --gpus N`, strong scaling at global batch 8192)\n")
+    out.append("Train column: Soft-Intro-TC images/s of the bench's training leg -- BASELINE configs[1] shape (64x64, z 128, batch 64) at N = 1, "
+               "configs[4] shape (128x128, z 256, batch 32 per GPU, data parallel) at N > 1, so the N = 1 entry is not the base of the others.\n")
     out.append("| N | ms / step | log-densities/s | efficiency vs N=1 | drop-in (eager) ms | e2e ms | e2e drop-in ms | train images/s | file |")
     out.append("|---|---|---|---|---|---|---|---|---|")
     base = None
