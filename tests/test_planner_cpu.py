@@ -41,7 +41,8 @@ SRC = textwrap.dedent(r"""
             if (rc) { std::printf("FAIL rc=%d blocks=%lld T=%d slots=%d target=%d\n", rc, (long long)b, T, sl, tg); return 1; }
         }
         // whole plans for shapes the tests and the bench use
-        const int shapes[][3] = {{8192, 8192, 128}, {1024, 8192, 128}, {2, 2, 4}, {37, 37, 20}, {24, 24, 512}, {4096, 32768, 512}, {1, 8, 3}};
+        const int shapes[][3] = {{8192, 8192, 128}, {1024, 8192, 128}, {2, 2, 4}, {37, 37, 20}, {24, 24, 512}, {4096, 32768, 512}, {1, 8, 3},
+                                   {4096, 4096, 64}, {4000, 4000, 20}, {1000, 1000, 128}, {512, 4096, 256}, {64, 64, 128}, {3, 3, 128}};
         for (auto& sh : shapes) {
             Plan p;
             if (!make_plan(p, sh[0], sh[1], sh[2], 4u, 148)) { std::printf("FAIL make_plan\n"); return 1; }
