@@ -285,8 +285,8 @@ long long tcelbo_launch_count(void);
  * the events are cudaEvent_t handles owned by the caller. */
 int tcelbo_profile_events(int kernel_id, void* start_event, void* stop_event);
 /* Tuning points for tools/tune_bwd.py; 0 restores the shipped choice of every key.  Keys: "bwd_variant" (tuning points of the fused
- * backward sweep), "bwd_seg_tiles" / "fwd_seg_tiles" (column tiles per CTA of the balanced-segment grids), "fwd_map" (1 = 32 dims
- * per lane in the forward sweep for every D), "fwd_wave" (CTAs per SM the forward grid is sized in waves of).  Unknown key:
+ * backward sweep), "bwd_seg_tiles" / "fwd_seg_tiles" (column tiles per CTA of the balanced-segment grids), "fwd_map" (1 = round 1's 32 dims
+ * per lane in the forward sweep), "fwd_wave" (CTAs per SM the forward grid is sized in waves of).  Unknown key:
  * TCELBO_ERR_INVALID.  Environment: TCELBO_PDL=0 launches the kernels without programmatic dependent launch. */
 int tcelbo_set_tuning(const char* key, int value);
 /* MUFU.EX2 saturation probe: `ctas` blocks of 256 threads, 8*iters dependent-chain ex2 per thread. */

@@ -233,13 +233,13 @@ __device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt,
 // JTS: columns per tile (0 = as many as fit kTileFloats, at most 32); KCH: 16-byte chunks (4 dims) per lane -- 4 (16 dims per
 // lane, 128 registers, 4 CTAs per SM) for D <= 128, 8 (32 dims per lane, 168 registers, 3 CTAs per SM) for wider latents and for
 // the small-problem instantiation; MINB: CTAs per SM
-template <int LPR, int JTS, int KCH = 8, int MINB = 3>
-__global__ void __launch_bounds__(kFwdWarps * 32, MINB)
+template <int LPR, int JTS, int KCH = 8, int MINB = 3, int NWF = kFwdWarps>
+__global__ void __launch_bounds__(NWF * 32, MINB)
 tc_fwd_kernel(const FwdArgs a) {
     pdl_trigger(); pdl_wait();                               // programmatic dependent launch, tc_common.cuh
     constexpr int DP = 4 * KCH * LPR;
     constexpr int RPW = 32 / LPR;
-    constexpr int ROWS = kFwdWarps * RPW;
+    constexpr int ROWS = NWF * RPW;
     constexpr int JT = JTS > 0 ? JTS : ((kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP));
     constexpr int TILE = JT * DP;
     constexpr int G = LPR < 4 ? LPR : 4;
@@ -306,7 +306,7 @@ tc_fwd_kernel(const FwdArgs a) {
     load_row();
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], kFwdWarps); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NWF); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -517,7 +517,7 @@ static inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
     return (int)g;
 }
 
-template <int LPR, int JTS, int KCH = 8, int MINB = 3>
+template <int LPR, int JTS, int KCH = 8, int MINB = 3, int NWF = kFwdWarps>
 static cudaError_t launch_fwd_t(const Plan& p, const FwdArgs& a, cudaStream_t st) {
     constexpr int DP = 4 * KCH * LPR;
     constexpr int JT = JTS > 0 ? JTS : ((kTileFloats / DP) > 32 ? 32 : (kTileFloats / DP));
@@ -525,12 +525,12 @@ static cudaError_t launch_fwd_t(const Plan& p, const FwdArgs& a, cudaStream_t st
     static PerDevice configured_on;
     int& configured = configured_on.cur();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<LPR, JTS, KCH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_fwd_kernel<LPR, JTS, KCH, MINB, NWF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = 1;
     }
     LaunchScope scope(kKernFwd, st);
-    return launch_pdl(tc_fwd_kernel<LPR, JTS, KCH, MINB>, dim3(p.seg_fwd.n_ctas), dim3(kFwdWarps * 32), smem, st, a);
+    return launch_pdl(tc_fwd_kernel<LPR, JTS, KCH, MINB, NWF>, dim3(p.seg_fwd.n_ctas), dim3(NWF * 32), smem, st, a);
 }
 
 cudaError_t launch_publish(const float* src, int64_t ld, int b_loc, int d, float* dst, unsigned int* epoch, cudaStream_t st) {
@@ -569,11 +569,13 @@ cudaError_t launch_fwd(const Plan& p, const FwdArgs& a, cudaStream_t st) {
             default: return cudaErrorInvalidValue;
         }
     }
-    if (p.fwd_kch == 4) {                // D <= 128: 16 dims per lane, 4 CTAs per SM (<= 128 registers)
+    if (p.fwd_kch == 4) {                // 16 dims per lane, 16 warps per SM (<= 128 registers)
         switch (p.fwd_lpr) {
             case 2:  return launch_fwd_t<2, 0, 4, 4>(p, a, st);
             case 4:  return launch_fwd_t<4, 0, 4, 4>(p, a, st);
             case 8:  return launch_fwd_t<8, 0, 4, 4>(p, a, st);
+            case 16: return launch_fwd_t<16, 0, 4, 2, 8>(p, a, st);      // D = 256 / 512: 8 warps per CTA keep 16 / 8 rows per CTA
+            case 32: return launch_fwd_t<32, 0, 4, 2, 8>(p, a, st);
             default: return cudaErrorInvalidValue;
         }
     }

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 
 namespace tcelbo {
 
@@ -66,7 +67,7 @@ struct Plan {
     // backward scratch (its own buffer, so the forward workspace stays immutable and backward can be re-run)
     size_t boff_gps, boff_gj, boff_gk, boff_A, boff_CR, boff_G, bwd_bytes;
     bool save, var_col;
-    int fwd_lpr, fwd_kch;      // forward sweep mapping: lanes per row, 16-byte chunks (4 dims) per lane
+    int fwd_lpr, fwd_kch, fwd_warps;   // forward sweep mapping: lanes per row, 16-byte chunks (4 dims) per lane, warps per CTA
     bool small;                // fewer work units than SMs with the standard tiles: small-tile / few-rows instantiations
 };
 
@@ -110,7 +111,8 @@ inline Segments plan_segments(int64_t n_blocks, int tiles_per_block, int slots, 
 }
 
 inline int& fwd_seg_target() { static int v = 0; return v; }    // tuning: forward segment length in column tiles (0 = default)
-inline int& fwd_map_tuning() { static int v = 0; return v; }    // tools/tune_bwd.py --fwd-map: 1 = 32 dims per lane everywhere (round-1 mapping)
+// tools/tune_bwd.py --fwd-map (or TCELBO_FWD_MAP): 1 = 32 dims per lane everywhere (round-1 mapping)
+inline int& fwd_map_tuning() { static int v = [] { const char* e = std::getenv("TCELBO_FWD_MAP"); return e ? std::atoi(e) : 0; }(); return v; }
 inline int& fwd_wave_tuning() { static int v = 0; return v; }   // tuning: CTAs per SM the forward grid is sized for (0 = as resident: 4 / 3)
 
 // `sms` = multiprocessor count of the current device (148 on B200).
@@ -123,27 +125,28 @@ inline bool make_plan(Plan& p, int b_loc, int b_glob, int d, uint32_t flags, int
     p.save = (flags & 4u) != 0;
     p.var_col = (flags & 2u) != 0;
     // ---- forward: a CTA owns fwd_rows rows and a contiguous range of columns
-    // forward mapping: lanes per row x 16-byte chunks per lane.  32 dims per lane (dp/32 lanes per row, 3 CTAs per SM) is the
-    // general one; D <= 128 uses 16 dims per lane (dp/16 lanes per row), which fits 4 CTAs per SM -- wider latents do not, because
-    // halving the rows per CTA doubles the L2 -> SM tile traffic.  Small problems (BASELINE cfg 1 / 2: B = 3 / 64) keep the general
-    // mapping with 4-column tiles, so that row blocks x tiles still gives every SM a CTA.
+    // forward mapping: lanes per row x 16-byte chunks per lane.  Shipped: 16 dims per lane (dp/16 lanes per row, 128 registers,
+    // 16 warps per SM) -- 4 warps per CTA for D <= 128, 8 warps per CTA for wider latents, so that a CTA still owns 16 (D = 256) /
+    // 8 (D = 512) rows and the L2 -> SM traffic of the column tiles does not grow.  Small problems (BASELINE cfg 1 / 2: B = 3 / 64)
+    // and the column-variance sweeps keep round 1's 32 dims per lane (dp/32 lanes per row, 3 CTAs of 4 warps per SM); the small
+    // ones with 4-column tiles, so that row blocks x tiles still gives every SM a CTA.
     // Rows pad to whole forward row blocks, columns to whole 32-column tiles; the column-variance sweeps keep the 128-row padding
     // their uniform grids were written for.
-    auto set_map = [&](int lpr, int kch) {
-        p.fwd_lpr = lpr; p.fwd_kch = kch;
-        p.fwd_rows = kFwdWarps * (32 / lpr);
+    auto set_map = [&](int lpr, int kch, int warps) {
+        p.fwd_lpr = lpr; p.fwd_kch = kch; p.fwd_warps = warps;
+        p.fwd_rows = warps * (32 / lpr);
         const int row_pad = p.var_col ? kRowPad : (p.fwd_rows > kColPad ? p.fwd_rows : kColPad);
         p.bl_pad = (int)round_up(b_loc, row_pad);
         p.n_rb_fwd = p.bl_pad / p.fwd_rows;
     };
-    set_map(p.dpt, 8);
+    set_map(p.dpt, 8, kFwdWarps);
     p.bg_pad = (int)round_up(b_glob, p.var_col ? kRowPad : kColPad);
     p.jt = kTileFloats / dp;                                   // 128 .. 8
     if (p.jt > 32) p.jt = 32;
     p.small = !p.var_col && (int64_t)p.n_rb_fwd * (p.bg_pad / p.jt) < sms;
     if (p.small) p.jt = kSmallTile;
-    else if (!p.var_col && dp <= 128 && fwd_map_tuning() == 0) set_map(dp / 16, 4);
-    const int fwd_res = fwd_wave_tuning() > 0 ? fwd_wave_tuning() : (p.fwd_kch == 4 ? 4 : 3);   // resident CTAs per SM: wave size
+    else if (!p.var_col && fwd_map_tuning() == 0) set_map(dp / 16, 4, dp <= 128 ? kFwdWarps : 8);
+    const int fwd_res = fwd_wave_tuning() > 0 ? fwd_wave_tuning() : (p.fwd_kch == 4 ? 16 / p.fwd_warps : 3);   // resident CTAs per SM: wave size
     choose_splits(p.n_rb_fwd, sms * 3, p.bg_pad, p.jt, 4, p.n_js_fwd, p.js_len_fwd);
     p.tiles_fwd = p.bg_pad / p.jt;
     p.seg_fwd = plan_segments(p.n_rb_fwd, p.tiles_fwd, sms * fwd_res, fwd_seg_target() > 0 ? fwd_seg_target() : 21);

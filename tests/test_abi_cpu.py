@@ -43,7 +43,7 @@ def test_workspace_planner_without_gpu():
 
 def test_tuning_keys_without_gpu():
     """tcelbo_set_tuning: the documented keys are accepted, an unknown key is an error; the forward mapping key changes the
-    planner's row padding for D <= 128 (16 rows per CTA with 16 dims per lane, 32 with 32 dims per lane) and nothing for D = 512."""
+    planner's row padding for D <= 128 (16 rows per CTA with 16 dims per lane, 32 with 32 dims per lane)."""
     from intro_tc_vae_b200 import _lib
     lib = _lib.load()
     flags = _lib.SAVE_FOR_BACKWARD
@@ -56,7 +56,6 @@ def test_tuning_keys_without_gpu():
         assert lib.tcelbo_set_tuning(b"fwd_map", 1) == 0
         wide = [lib.tcelbo_workspace_bytes(1000, 8192, d, flags) for d in (20, 64, 128, 512)]
         assert all(w > 0 for w in shipped + wide)
-        assert shipped[3] == wide[3]
         assert shipped[:3] != wide[:3]
     finally:
         lib.tcelbo_set_tuning(b"fwd_map", 0)
