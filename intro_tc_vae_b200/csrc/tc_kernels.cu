@@ -230,9 +230,10 @@ __device__ __forceinline__ void fwd_tile(const float* __restrict__ tile, int jt,
     }
 }
 
-// JTS: columns per tile (0 = as many as fit kTileFloats, at most 32); KCH: 16-byte chunks (4 dims) per lane -- 4 (16 dims per
-// lane, 128 registers, 4 CTAs per SM) for D <= 128, 8 (32 dims per lane, 168 registers, 3 CTAs per SM) for wider latents and for
-// the small-problem instantiation; MINB: CTAs per SM
+// JTS: columns per tile (0 = as many as fit kTileFloats, at most 32); KCH: 16-byte chunks (4 dims) per lane -- 4 in the shipped
+// mapping (16 dims per lane, 128 registers, 16 warps per SM), 8 (32 dims per lane, 168 registers, 3 CTAs of 4 warps per SM) in the
+// small-problem instantiation and the fwd_map = 1 tuning point; MINB: CTAs per SM; NWF: warps per CTA (8 for D >= 256, so that
+// a CTA keeps 16 / 8 rows)
 template <int LPR, int JTS, int KCH = 8, int MINB = 3, int NWF = kFwdWarps>
 __global__ void __launch_bounds__(NWF * 32, MINB)
 tc_fwd_kernel(const FwdArgs a) {

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="rows of this shard (default: the whole batch); emulates one rank of a row-sharded job")
     ap.add_argument("--fwd-seg", default="", help="comma list of forward segment-length targets (column tiles per CTA)")
     ap.add_argument("--fwd-wave", default="", help="comma list: CTAs per SM the forward grid is sized for (0 = as resident)")
-    ap.add_argument("--fwd-map", default="", help="comma list: 0 = shipped forward mapping (16 dims per lane for D <= 128), 1 = 32 dims per lane everywhere")
+    ap.add_argument("--fwd-map", default="", help="comma list: 0 = shipped forward mapping (16 dims per lane), 1 = round 1's 32 dims per lane")
     ap.add_argument("--seg", default="0", help="comma list of segment-length targets (column tiles per CTA; 0 = default)")
     args = ap.parse_args()
     lib = _lib.load()
